@@ -1,0 +1,112 @@
+"""Pin the CPU oracle against the golden fixtures produced by the unmodified reference
+(tests/golden/make_golden.py) and against the installed HF BertModel."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import morec_oracle as O
+
+CASES = ["id_small_collide", "id_cfg1_shape", "text_tiny", "text_tiny_collide"]
+
+
+def run_oracle(g, dtype=torch.float32, grad=False):
+    m = g["meta"]
+    p = {k: v.to(dtype).clone().requires_grad_(grad) if v.is_floating_point() else v for k, v in g["state_dict"].items()}
+    out = O.model_forward(p, g["ids"], g["items"], g["log_mask"], g["pop_prob"], use_modal=m["modal"],
+                          n_heads_user=m["heads"], n_heads_bert=(m["bert_cfg"] or {}).get("num_attention_heads", 0))
+    return p, out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_forward(goldens, name):
+    g = goldens[name]
+    _, out = run_oracle(g)
+    assert abs(float(out.loss) - float(g["loss"])) <= 1e-5
+    nonpad = (g["ids"].reshape(-1) != 0)
+    assert torch.allclose(out.score_embs[nonpad], g["score_embs"][nonpad], atol=2e-5, rtol=1e-5)
+    pv = g["prec_vec"].reshape(out.prec_vec.shape)
+    valid = O.valid_rows(g["log_mask"])
+    assert torch.allclose(out.prec_vec[valid], pv[valid], atol=5e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_grads(goldens, name):
+    g = goldens[name]
+    p, out = run_oracle(g, grad=True)
+    out.loss.backward()
+    for k, gref in g["grads"].items():
+        if k.startswith("bert_encoder") and "pooler" in k:
+            continue
+        got = p[k].grad
+        assert got is not None, k
+        scale = float(gref.abs().max()) + 1e-12
+        if k == "id_embedding.weight":
+            # reference nn.Embedding(padding_idx=0) zeroes the grad of row 0; pad slots get exactly 0 anyway
+            assert float(got[0].abs().max()) == 0.0
+        assert float((got - gref).abs().max()) <= 2e-4 * scale + 1e-7, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_mask_closed_form_equals_loops(goldens, name):
+    g = goldens[name]
+    if g["ids"].numel() > 400:
+        ids = g["ids"][:5, -7:].clone()
+    else:
+        ids = g["ids"]
+    assert torch.equal(O.reject_mask_closed_form(ids), O.reject_mask_loops(ids))
+
+
+def test_mask_edge_cases():
+    # fully padded user except the mandatory last item, duplicates inside a user, same item across users, B=1
+    ids = torch.tensor([[0, 0, 0, 5], [5, 5, 7, 5], [0, 7, 5, 9]])
+    a, b = O.reject_mask_closed_form(ids), O.reject_mask_loops(ids)
+    assert torch.equal(a, b)
+    one = torch.tensor([[0, 3, 3, 4]])
+    assert torch.equal(O.reject_mask_closed_form(one), O.reject_mask_loops(one))
+    # target column of a valid row is never masked
+    B, Lp1 = ids.shape
+    tgt = O.ce_labels(B, Lp1 - 1)
+    v = O.valid_rows(O.log_mask_from_ids(ids))
+    assert not a[torch.arange(a.shape[0]), tgt][v].any()
+
+
+def test_labels_and_logmask():
+    assert O.ce_labels(2, 3).tolist() == [1, 2, 3, 5, 6, 7]
+    ids = torch.tensor([[0, 0, 4, 9], [1, 2, 3, 4]])
+    assert O.log_mask_from_ids(ids).tolist() == [[0, 0, 1], [1, 1, 1]]
+
+
+def test_bert_restatement_matches_hf():
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(0)
+    cfg = BertConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                     vocab_size=100, max_position_embeddings=32)
+    m = BertModel(cfg).eval()
+    ids = torch.randint(1, 100, (5, 9))
+    am = torch.ones(5, 9, dtype=torch.long)
+    am[1, 5:] = 0
+    am[3, 2:] = 0
+    ids = ids * am
+    with torch.no_grad():
+        ref = m(input_ids=ids, attention_mask=am)[0]
+        got = O.bert_forward(dict(m.state_dict()), ids, am, 4)
+    # only compare tokens that can matter (valid tokens); pad-token rows are never consumed
+    assert torch.allclose(got[am.bool()], ref[am.bool()], atol=2e-5, rtol=1e-5)
+
+
+def test_synth_batch_properties():
+    d = O.synth_batch(16, 25, 5000, 30, 3, modal=True)
+    ids = d["ids"]
+    assert ids.shape == (16, 26) and (ids[:, -1] != 0).all()
+    nz = (ids != 0).sum(1)
+    assert int(nz.min()) >= 3
+    # left padded: zeros then non-zeros
+    for r in ids:
+        k = int((r != 0).nonzero()[0])
+        assert (r[:k] == 0).all() and (r[k:] != 0).all()
+    assert (d["pop_prob"][ids.reshape(-1)] > 0).all() and float(d["pop_prob"][0]) == 1.0
+    assert abs(float(d["pop_prob"][1:].sum()) - 1.0) < 1e-9
+    it = d["items"]
+    assert it.shape == (16 * 26, 60)
+    assert (it[ids.reshape(-1) == 0] == 0).all()
+    assert (it[ids.reshape(-1) != 0, 0] == 101).all()
