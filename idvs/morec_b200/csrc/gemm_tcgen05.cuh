@@ -1,0 +1,405 @@
+// Persistent, warp-specialised tcgen05 GEMM mainloop for sm_100a (header: kernel template + launcher template).
+//
+//   C[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//
+//   * operands arrive by TMA (SWIZZLE_128B) into a multi-stage shared-memory ring,
+//   * one elected thread issues tcgen05.mma (kind::tf32 on fp32 storage, or kind::f16 on bf16 storage); fp32
+//     accumulators live in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1,
+//   * four epilogue warps read TMEM (tcgen05.ld 32x32b) and run the Epilogue functor (fused bias / GELU / ReLU /
+//     activation-gradient / in-batch-CE partials ...); outputs are staged as 32-row x 128-byte sub-tiles in
+//     swizzled shared memory and written by TMA store (or TMA reduce-add for split-K accumulation),
+//   * either operand may be K-major ([rows, K] row-major) or MN-major ([K, rows] row-major), so forward, dgrad and
+//     wgrad of a linear layer all run on this one kernel without materialising a transpose.
+//
+// Reference op sites this replaces (eager cuBLAS + separate elementwise kernels in the reference):
+//   inbatch_sasrec_e2e_text/model/encoders.py:68-70 (HF BertModel linears + fc), model/modules.py:14-17,52-63
+//   (SASRec linears), model/model.py:49 (scoring matmul; the CE epilogues live in inbatch_ce.cu).
+#pragma once
+#include "common.cuh"
+
+namespace morec {
+
+// swizzle32: false -> SWIZZLE_128B (16B atoms), true -> SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for
+// MN-major 32-bit (tf32) operands: UMMA layout type SWIZZLE_128B_BASE32B, 4-row x 128B swizzle atoms)
+int make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inner, uint64_t outer,
+                 uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle32 = false);
+
+struct GemmArgs {
+    const void* A;
+    const void* B;
+    void* C;       // primary output (may be null for epilogues that store nothing)
+    void* C2;      // secondary output (e.g. pre-activation), same shape/ld as C
+    int M, N, K;
+    int lda, ldb, ldc;     // leading dimensions in elements
+    int a_mn, b_mn;        // 0: operand is [rows, K] row-major (K-major); 1: [K, rows] row-major (MN-major)
+    int dtype;             // 0: fp32 storage / kind::tf32, 1: bf16 storage / kind::f16
+    int out_bf16;          // output element type of C/C2 (0: fp32, 1: bf16)
+    int accumulate;        // 1: C += result via TMA reduce-add (C must be fp32); enables split-K
+    int allow_split_k;
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int kThreads = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-7 epilogue
+constexpr int kEpiWarps = 4;
+constexpr int kEpiBufBytes = 4096;   // one 32-row x 128B sub-tile (32 fp32 or 64 bf16 columns), SWIZZLE_128B
+constexpr int kEpiBufsPerWarp = 4;
+
+struct TileSched {
+    int M, N, K;
+    int num_kb, kb_per_split, splits;
+    int m_tiles, n_tiles;
+    int a_mn, b_mn;
+    int accumulate;
+    int out_bf16;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2 /* SWIZZLE_128B */) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+    return d;
+}
+
+template <int KIND, int BLOCK_N>
+struct Cfg {
+    static constexpr int ELEM = KIND == 0 ? 4 : 2;
+    static constexpr int BLOCK_K = 128 / ELEM;          // K elements per stage (one 128B swizzle row)
+    static constexpr int UMMA_K = 32 / ELEM;            // 8 (tf32) / 16 (bf16)
+    static constexpr int CHUNK = 128 / ELEM;            // MN elements per 128B row of an MN-major tile
+    static constexpr int A_BYTES = BLOCK_M * 128;
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_BYTES = kEpiWarps * kEpiBufsPerWarp * kEpiBufBytes;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int SMEM_LIMIT = 227 * 1024;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;       // double-buffered fp32 accumulator
+    static_assert(TMEM_COLS <= 512, "TMEM overflow");
+    static_assert(STAGES >= 2, "not enough smem stages");
+};
+
+// Staging + TMA store of one 32-row sub-tile held as 32 fp32 per thread (thread == row).
+// fp32 output : 32 columns  -> one 128B row, stored immediately.
+// bf16 output : 32 columns  -> half a 128B row; the store is issued after the odd chunk.
+struct EpiStore {
+    uint8_t* bufs;     // this warp's kEpiBufsPerWarp staging buffers
+    int buf;           // rotating index
+    int lane;
+    __device__ __forceinline__ void begin() {
+        // conservative for two interleaved output streams (C2 and C): two buffers are filled before either commit
+        if (lane == 0) tma_store_wait_read<kEpiBufsPerWarp - 2>();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void put_f32(const float (&x)[32], int slot) {
+        uint8_t* rowp = bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int pj = j ^ (lane & 7);
+            *reinterpret_cast<float4*>(rowp + pj * 16) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
+    }
+    __device__ __forceinline__ void put_bf16(const float (&x)[32], int half, int slot) {
+        uint8_t* rowp = bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pj = (half * 4 + j) ^ (lane & 7);
+            __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]);
+            __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
+            __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]);
+            __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+            u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+            *reinterpret_cast<uint4*>(rowp + pj * 16) = u;
+        }
+    }
+    __device__ __forceinline__ void commit(const CUtensorMap* tm, int col0, int row0, bool reduce_add, int slot = 0) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t src = smem_u32(bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes);
+            if (reduce_add) tma_reduce_add_2d(tm, src, col0, row0);
+            else tma_store_2d(tm, src, col0, row0);
+            tma_store_commit();
+        }
+    }
+    __device__ __forceinline__ void advance(int n) { buf = (buf + n) % kEpiBufsPerWarp; }
+    // One 32-column chunk `c` of the tile whose first column is n0.  `slot`/`nslots`: an epilogue with two output
+    // streams emits slot 1 (C2) then slot 0 (C) for every chunk; the buffer ring advances once per chunk (fp32) or
+    // once per chunk pair (bf16) after the LAST slot has been emitted.
+    __device__ __forceinline__ void emit(const CUtensorMap* tm, const float (&x)[32], int c, int n0, int row0,
+                                         bool out_bf16, bool reduce_add, int slot = 0, int nslots = 1) {
+        const bool first = slot == nslots - 1, last = slot == 0;
+        if (!out_bf16) {
+            if (first) begin();
+            put_f32(x, slot);
+            commit(tm, n0 + c * 32, row0, reduce_add, slot);
+            if (last) advance(nslots);
+        } else {
+            if ((c & 1) == 0 && first) begin();
+            put_bf16(x, c & 1, slot);
+            if (c & 1) {
+                commit(tm, n0 + (c - 1) * 32, row0, false, slot);
+                if (last) advance(nslots);
+            }
+        }
+    }
+};
+
+// Epilogue functor contract:
+//   struct Epi { struct Params {...};
+//     static __device__ void tile(const Params&, const CUtensorMap& tmC, const CUtensorMap& tmC2, uint32_t taddr,
+//                                 EpiStore& st, int m0, int q, int n0, int split, const TileSched& s); }
+//   taddr already includes the warp's lane quarter and the accumulator stage; thread `lane` owns row m0+q*32+lane.
+
+template <int KIND, int BLOCK_N, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TileSched p,
+            const typename Epi::Params ep) {
+    using C = Cfg<KIND, BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024B alignment for SWIZZLE_128B
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
+    uint64_t* full_bar = bars;                        // [STAGES]
+    uint64_t* empty_bar = bars + C::STAGES;           // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2]
+    uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmC2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull_bar[s]), 1);
+            mbar_init(smem_u32(&tempty_bar[s]), kEpiWarps);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w % p.splits;
+                const int tile = w / p.splits;
+                const int m0 = (tile / p.n_tiles) * BLOCK_M;
+                const int n0 = (tile % p.n_tiles) * BLOCK_N;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, C::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + C::A_BYTES;
+                    const int k0 = kb * C::BLOCK_K;
+                    if (!p.a_mn) {
+                        tma_load_2d(&tmA, fb, sa, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / C::CHUNK; ++c)
+                            tma_load_2d(&tmA, fb, sa + c * (C::BLOCK_K * 128), m0 + c * C::CHUNK, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(&tmB, fb, sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_N / C::CHUNK; ++c)
+                            tma_load_2d(&tmB, fb, sb + c * (C::BLOCK_K * 128), n0 + c * C::CHUNK, k0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A major [15], B major [16],
+        // N>>3 [17,23), M>>4 [24,29)
+        constexpr uint32_t fmt = KIND == 0 ? 2u : 1u;   // tf32 : bf16
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                               ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                               ((uint32_t)(BLOCK_M >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                if (lane == 0) {   // one fixed thread issues every MMA and commit of this CTA
+                    const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k) {
+                        // K-major : 32 bytes per UMMA_K inside the 128B swizzle row; SBO = 8 rows * 128B.
+                        // MN-major: UMMA_K k-rows of 128B each; LBO = next 128B chunk along MN, SBO = next 8 k-rows.
+                        // (tf32 MN-major uses the 32B-atom swizzle: 4 k-rows per atom -> SBO = 512B, layout type 1.)
+                        constexpr uint32_t mn_sbo = KIND == 0 ? 512 : 1024;
+                        constexpr uint32_t mn_lt = KIND == 0 ? 1 : 2;
+                        const uint64_t ad = p.a_mn ? make_smem_desc(sa + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
+                                                   : make_smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = p.b_mn ? make_smem_desc(sb + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
+                                                   : make_smem_desc(sb + k * 32, 16, 1024);
+                        tc_mma<KIND>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot when these MMAs retire
+                    if (kb == kb1 - 1) tc_commit(smem_u32(&tfull_bar[acc]));   // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp - 4;  // TMEM lane quarter == warp % 4
+        EpiStore st;
+        st.bufs = epi_base + q * (kEpiBufsPerWarp * kEpiBufBytes);
+        st.buf = 0;
+        st.lane = lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int tile = w / p.splits;
+            const int m0 = (tile / p.n_tiles) * BLOCK_M;
+            const int n0 = (tile % p.n_tiles) * BLOCK_N;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+            Epi::template tile<BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N, st, m0, q,
+                                        n0, split, p);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait<0>();
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher (template; instantiated per epilogue family)
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int BLOCK_N, class Epi>
+int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
+    using C = Cfg<KIND, BLOCK_N>;
+    constexpr int ELEM = C::ELEM;
+    const bool bf = KIND == 1;
+    CUtensorMap tmA, tmB, tmC, tmC2;
+    int rc;
+    if (!g.a_mn) rc = make_tmap_2d(&tmA, g.A, bf, g.K, g.M, (uint64_t)g.lda * ELEM, C::BLOCK_K, BLOCK_M);
+    else         rc = make_tmap_2d(&tmA, g.A, bf, g.M, g.K, (uint64_t)g.lda * ELEM, C::CHUNK, C::BLOCK_K, KIND == 0);
+    if (rc) return rc;
+    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, bf, g.K, g.N, (uint64_t)g.ldb * ELEM, C::BLOCK_K, BLOCK_N);
+    else         rc = make_tmap_2d(&tmB, g.B, bf, g.N, g.K, (uint64_t)g.ldb * ELEM, C::CHUNK, C::BLOCK_K, KIND == 0);
+    if (rc) return rc;
+    const int out_elem = g.out_bf16 ? 2 : 4;
+    const int out_cols = 128 / out_elem;
+    if (g.C) {
+        rc = make_tmap_2d(&tmC, g.C, g.out_bf16 != 0, g.N, g.M, (uint64_t)g.ldc * out_elem, out_cols, 32);
+        if (rc) return rc;
+    } else {
+        tmC = tmA;
+    }
+    if (g.C2) {
+        rc = make_tmap_2d(&tmC2, g.C2, g.out_bf16 != 0, g.N, g.M, (uint64_t)g.ldc * out_elem, out_cols, 32);
+        if (rc) return rc;
+    } else {
+        tmC2 = tmC;
+    }
+    if (g.accumulate && g.out_bf16) {
+        set_last_error("gemm: accumulate (TMA reduce-add) requires fp32 output");
+        return MOREC_ERR_ARG;
+    }
+
+    TileSched p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.num_kb = (g.K + C::BLOCK_K - 1) / C::BLOCK_K;
+    p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (g.N + BLOCK_N - 1) / BLOCK_N;
+    p.a_mn = g.a_mn; p.b_mn = g.b_mn;
+    p.accumulate = g.accumulate;
+    p.out_bf16 = g.out_bf16;
+    const int sms = num_sms();
+    int splits = 1;
+    if (g.accumulate && g.allow_split_k) {
+        const int tiles = p.m_tiles * p.n_tiles;
+        splits = sms / tiles;
+        if (splits < 1) splits = 1;
+        const int max_splits = p.num_kb / 8 > 0 ? p.num_kb / 8 : 1;   // keep >= 8 k-blocks per split
+        if (splits > max_splits) splits = max_splits;
+    }
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = total < sms ? total : sms;
+
+    auto kern = gemm_kernel<KIND, BLOCK_N, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+template <class Epi>
+int gemm_dispatch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
+    MOREC_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+    MOREC_CHECK_ARG(g.dtype == 0 || g.dtype == 1, "gemm: dtype must be 0 (fp32/tf32) or 1 (bf16)");
+    const bool wide = (g.N % 256 == 0) || g.N > 384;
+    if (g.dtype == 0) return wide ? gemm_launch<0, 256, Epi>(g, ep, stream) : gemm_launch<0, 128, Epi>(g, ep, stream);
+    return wide ? gemm_launch<1, 256, Epi>(g, ep, stream) : gemm_launch<1, 128, Epi>(g, ep, stream);
+}
+
+}  // namespace morec
