@@ -1,0 +1,416 @@
+// Short-sequence multi-head attention, forward and backward, for sequences of at most 32 tokens
+// (item titles: T = 30 word pieces, parameters.py:42; user histories: L <= 25..32, parameters.py:30).
+//
+// Replaces   HF BertSelfAttention  (call site model/encoders.py:68): softmax(QK^T/sqrt(d_h) + key-pad mask) V
+//            SASRec SelfAttention  (model/modules.py:27-31, mask model/encoders.py:23-28):
+//                                   softmax(QK^T/sqrt(d_k) + (k<=q & key valid ? 0 : -1e9)) V,  dropout on P
+// One warp owns one (sequence, head) pair; lane i owns query row i.  K / V / Q / dO are streamed through a
+// [32][64] fp32 shared-memory tile in head-dim chunks of 64 (any head_dim that is a multiple of 4 works: 16, 32, 64,
+// 256, 1024), rows are read by all lanes at the same address (broadcast, conflict-free) while each lane keeps its
+// own 64-wide slice of q / o / dq in registers.  The whole score row (<= 32 values) lives in registers, so the
+// softmax is exact two-pass fp32.  Packed (variable-length) batches are described by cu_seqlens; fixed-length
+// batches (SASRec) by seqlen + an optional [n_seq, seqlen] key-valid mask and a causal flag.
+#include "../../../include/morec_b200.h"
+#include "common.cuh"
+
+namespace morec {
+
+constexpr int AT_DCH = 64;      // head-dim chunk
+constexpr int AT_WARPS = 4;
+constexpr int AT_MAXL = 32;
+
+struct AttnParams {
+    const void *q, *k, *v, *o;        // o: forward output / backward: dO
+    void *dq, *dk, *dv;               // backward outputs (null in forward); forward writes `out`
+    void* out;
+    const int* cu_seqlens;            // [n_seq+1] or null
+    const float* key_mask;            // [n_seq, seqlen] (non-zero = valid key) or null
+    int causal;
+    int n_seq, seqlen, n_heads, head_dim, ld, ld_o;   // ld: q/k/v/dq/dk/dv row stride, ld_o: o/dO row stride
+    float scale, masked_add;
+    float dropout_p;
+    uint64_t seed, offset;
+};
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// cooperative (one warp) load of rows [row0, row0+len) x cols [col0, col0+w) into tile[32][AT_DCH] (fp32)
+template <typename T>
+__device__ __forceinline__ void load_tile(float* tile, const T* base, int ld, int row0, int len, int col0, int w,
+                                          int lane) {
+    for (int idx = lane; idx < len * w; idx += 32) {
+        const int r = idx / w, c = idx - r * w;
+        tile[r * AT_DCH + c] = ldf<T>(base + (size_t)(row0 + r) * ld + col0 + c);
+    }
+}
+
+__device__ __forceinline__ void seq_range(const AttnParams& p, int s, int& row0, int& len) {
+    if (p.cu_seqlens) { row0 = p.cu_seqlens[s]; len = p.cu_seqlens[s + 1] - row0; }
+    else { row0 = s * p.seqlen; len = p.seqlen; }
+    if (len > AT_MAXL) len = AT_MAXL;
+}
+
+// additive mask for (query i, key j) of sequence s
+__device__ __forceinline__ float mask_add(const AttnParams& p, int s, int i, int j) {
+    bool ok = true;
+    if (p.causal) ok = j <= i;
+    if (p.key_mask) ok = ok && (p.key_mask[(size_t)s * p.seqlen + j] != 0.f);
+    return ok ? 0.f : p.masked_add;
+}
+
+// scores + softmax for lane i: on return pr[j] = softmax_j (un-dropped probabilities), j < len
+template <typename T>
+__device__ __forceinline__ void scores_softmax(const AttnParams& p, float* tile, int s, int h, int row0, int len,
+                                               int lane, float (&pr)[AT_MAXL]) {
+    const T* Q = reinterpret_cast<const T*>(p.q);
+    const T* K = reinterpret_cast<const T*>(p.k);
+#pragma unroll
+    for (int j = 0; j < AT_MAXL; ++j) pr[j] = 0.f;
+    for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+        const int w = min(AT_DCH, p.head_dim - dc);
+        __syncwarp();
+        load_tile<T>(tile, K, p.ld, row0, len, h * p.head_dim + dc, w, lane);
+        __syncwarp();
+        float qv[AT_DCH];
+        if (lane < len) {
+            const T* qr = Q + (size_t)(row0 + lane) * p.ld + h * p.head_dim + dc;
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) qv[t] = t < w ? ldf<T>(qr + t) : 0.f;
+        } else {
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) qv[t] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < AT_MAXL; ++j) {
+            if (j < len) {
+                float acc = 0.f;
+                const float4* kr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+                const int nt = w >> 2;
+#pragma unroll
+                for (int t = 0; t < AT_DCH / 4; ++t) {
+                    if (t < nt) {
+                        const float4 kk = kr[t];
+                        acc += qv[4 * t] * kk.x + qv[4 * t + 1] * kk.y + qv[4 * t + 2] * kk.z + qv[4 * t + 3] * kk.w;
+                    }
+                }
+                pr[j] += acc;
+            }
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AT_MAXL; ++j) {
+        if (j < len) {
+            pr[j] = pr[j] * p.scale + mask_add(p, s, lane, j);
+            m = fmaxf(m, pr[j]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < AT_MAXL; ++j) {
+        if (j < len) { pr[j] = __expf(pr[j] - m); sum += pr[j]; }
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < AT_MAXL; ++j) pr[j] = j < len ? pr[j] * inv : 0.f;
+}
+
+// dropout keep mask bits for row (pair, i): bit j set = keep
+__device__ __forceinline__ uint32_t keep_bits(const AttnParams& p, int pair, int i, int len) {
+    if (!(p.dropout_p > 0.f)) return 0xffffffffu;
+    const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int g = 0; g < AT_MAXL / 4; ++g) {
+        if (4 * g < len) {
+            const uint4 r = Philox::gen(p.seed, p.offset + ((uint64_t)pair * AT_MAXL + i) * (AT_MAXL / 4) + g);
+            bits |= (uint32_t)(r.x >= th) << (4 * g);
+            bits |= (uint32_t)(r.y >= th) << (4 * g + 1);
+            bits |= (uint32_t)(r.z >= th) << (4 * g + 2);
+            bits |= (uint32_t)(r.w >= th) << (4 * g + 3);
+        }
+    }
+    return bits;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(const AttnParams p) {
+    __shared__ __align__(16) float tiles[AT_WARPS][AT_MAXL * AT_DCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tiles[warp];
+    const int n_pairs = p.n_seq * p.n_heads;
+    for (int pair = blockIdx.x * AT_WARPS + warp; pair < n_pairs; pair += gridDim.x * AT_WARPS) {
+        const int s = pair / p.n_heads, h = pair - s * p.n_heads;
+        int row0, len;
+        seq_range(p, s, row0, len);
+        if (len <= 0) continue;
+        float pr[AT_MAXL];
+        scores_softmax<T>(p, tile, s, h, row0, len, lane, pr);
+        if (p.dropout_p > 0.f) {
+            const uint32_t kb = keep_bits(p, pair, lane, len);
+            const float sc = 1.f / (1.f - p.dropout_p);
+#pragma unroll
+            for (int j = 0; j < AT_MAXL; ++j) pr[j] = ((kb >> j) & 1u) ? pr[j] * sc : 0.f;
+        }
+        const T* V = reinterpret_cast<const T*>(p.v);
+        T* O = reinterpret_cast<T*>(p.out);
+        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+            const int w = min(AT_DCH, p.head_dim - dc);
+            __syncwarp();
+            load_tile<T>(tile, V, p.ld, row0, len, h * p.head_dim + dc, w, lane);
+            __syncwarp();
+            float ov[AT_DCH];
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) ov[t] = 0.f;
+#pragma unroll
+            for (int j = 0; j < AT_MAXL; ++j) {
+                if (j < len) {
+                    const float4* vr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+                    const float pj = pr[j];
+#pragma unroll
+                    for (int t = 0; t < AT_DCH / 4; ++t) {
+                        const float4 vv = vr[t];
+                        ov[4 * t] += pj * vv.x; ov[4 * t + 1] += pj * vv.y; ov[4 * t + 2] += pj * vv.z; ov[4 * t + 3] += pj * vv.w;
+                    }
+                }
+            }
+            if (lane < len) {
+                T* orow = O + (size_t)(row0 + lane) * p.ld_o + h * p.head_dim + dc;
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t)
+                    if (t < w) stf<T>(orow + t, ov[t]);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) float at_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = at_smem + warp * (AT_MAXL * AT_DCH);                                   // [32][64] stream tile
+    float* Pw = at_smem + AT_WARPS * (AT_MAXL * AT_DCH) + warp * (2 * AT_MAXL * 33);      // P~[i][j] (dropped, rescaled)
+    float* dSw = Pw + AT_MAXL * 33;                                                      // dS[i][j] * scale
+    const int n_pairs = p.n_seq * p.n_heads;
+    const T* Q = reinterpret_cast<const T*>(p.q);
+    const T* K = reinterpret_cast<const T*>(p.k);
+    const T* V = reinterpret_cast<const T*>(p.v);
+    const T* dO = reinterpret_cast<const T*>(p.o);
+    T* dQ = reinterpret_cast<T*>(p.dq);
+    T* dK = reinterpret_cast<T*>(p.dk);
+    T* dV = reinterpret_cast<T*>(p.dv);
+    for (int pair = blockIdx.x * AT_WARPS + warp; pair < n_pairs; pair += gridDim.x * AT_WARPS) {
+        const int s = pair / p.n_heads, h = pair - s * p.n_heads;
+        int row0, len;
+        seq_range(p, s, row0, len);
+        if (len <= 0) continue;
+        const int col_h = h * p.head_dim;
+        float pr[AT_MAXL];
+        scores_softmax<T>(p, tile, s, h, row0, len, lane, pr);
+        // ---- dP~[i][j] = dO_i . V_j
+        float dp[AT_MAXL];
+#pragma unroll
+        for (int j = 0; j < AT_MAXL; ++j) dp[j] = 0.f;
+        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+            const int w = min(AT_DCH, p.head_dim - dc);
+            __syncwarp();
+            load_tile<T>(tile, V, p.ld, row0, len, col_h + dc, w, lane);
+            __syncwarp();
+            float gv[AT_DCH];
+            if (lane < len) {
+                const T* gr = dO + (size_t)(row0 + lane) * p.ld_o + col_h + dc;
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t) gv[t] = t < w ? ldf<T>(gr + t) : 0.f;
+            } else {
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t) gv[t] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < AT_MAXL; ++j) {
+                if (j < len) {
+                    float acc = 0.f;
+                    const float4* vr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+                    const int nt = w >> 2;
+#pragma unroll
+                    for (int t = 0; t < AT_DCH / 4; ++t) {
+                        if (t < nt) {
+                            const float4 vv = vr[t];
+                            acc += gv[4 * t] * vv.x + gv[4 * t + 1] * vv.y + gv[4 * t + 2] * vv.z + gv[4 * t + 3] * vv.w;
+                        }
+                    }
+                    dp[j] += acc;
+                }
+            }
+        }
+        // ---- softmax backward (with dropout on P): dS = P * (dP - sum_k P_k dP_k), dP = keep * dP~ / (1-p)
+        {
+            const uint32_t kb = keep_bits(p, pair, lane, len);
+            const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+            float dsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < AT_MAXL; ++j) {
+                const float keep = ((kb >> j) & 1u) ? sc : 0.f;
+                dp[j] *= keep;                 // dP (w.r.t. un-dropped probabilities)
+                dsum += pr[j] * dp[j];
+                Pw[lane * 33 + j] = pr[j] * keep;   // P~ for dV
+            }
+#pragma unroll
+            for (int j = 0; j < AT_MAXL; ++j) dSw[lane * 33 + j] = (lane < len && j < len) ? pr[j] * (dp[j] - dsum) * p.scale : 0.f;
+            if (lane >= len) {
+#pragma unroll
+                for (int j = 0; j < AT_MAXL; ++j) Pw[lane * 33 + j] = 0.f;
+            }
+        }
+        __syncwarp();
+        // ---- dQ_i = sum_j dS_ij K_j        (lane = query i; K chunk broadcast from smem)
+        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+            const int w = min(AT_DCH, p.head_dim - dc);
+            __syncwarp();
+            load_tile<T>(tile, K, p.ld, row0, len, col_h + dc, w, lane);
+            __syncwarp();
+            float acc[AT_DCH];
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
+            for (int j = 0; j < len; ++j) {
+                const float d = dSw[lane * 33 + j];
+                const float4* kr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+#pragma unroll
+                for (int t = 0; t < AT_DCH / 4; ++t) {
+                    const float4 kk = kr[t];
+                    acc[4 * t] += d * kk.x; acc[4 * t + 1] += d * kk.y; acc[4 * t + 2] += d * kk.z; acc[4 * t + 3] += d * kk.w;
+                }
+            }
+            if (lane < len) {
+                T* r = dQ + (size_t)(row0 + lane) * p.ld + col_h + dc;
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t)
+                    if (t < w) stf<T>(r + t, acc[t]);
+            }
+        }
+        // ---- dK_j = sum_i dS_ij Q_i        (lane = key j; Q chunk broadcast from smem)
+        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+            const int w = min(AT_DCH, p.head_dim - dc);
+            __syncwarp();
+            load_tile<T>(tile, Q, p.ld, row0, len, col_h + dc, w, lane);
+            __syncwarp();
+            float acc[AT_DCH];
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
+            for (int i = 0; i < len; ++i) {
+                const float d = dSw[i * 33 + lane];
+                const float4* qr = reinterpret_cast<const float4*>(tile + i * AT_DCH);
+#pragma unroll
+                for (int t = 0; t < AT_DCH / 4; ++t) {
+                    const float4 qq = qr[t];
+                    acc[4 * t] += d * qq.x; acc[4 * t + 1] += d * qq.y; acc[4 * t + 2] += d * qq.z; acc[4 * t + 3] += d * qq.w;
+                }
+            }
+            if (lane < len) {
+                T* r = dK + (size_t)(row0 + lane) * p.ld + col_h + dc;
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t)
+                    if (t < w) stf<T>(r + t, acc[t]);
+            }
+        }
+        // ---- dV_j = sum_i P~_ij dO_i       (lane = key j; dO chunk broadcast from smem)
+        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
+            const int w = min(AT_DCH, p.head_dim - dc);
+            __syncwarp();
+            load_tile<T>(tile, dO, p.ld_o, row0, len, col_h + dc, w, lane);
+            __syncwarp();
+            float acc[AT_DCH];
+#pragma unroll
+            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
+            for (int i = 0; i < len; ++i) {
+                const float d = Pw[i * 33 + lane];
+                const float4* gr = reinterpret_cast<const float4*>(tile + i * AT_DCH);
+#pragma unroll
+                for (int t = 0; t < AT_DCH / 4; ++t) {
+                    const float4 gg = gr[t];
+                    acc[4 * t] += d * gg.x; acc[4 * t + 1] += d * gg.y; acc[4 * t + 2] += d * gg.z; acc[4 * t + 3] += d * gg.w;
+                }
+            }
+            if (lane < len) {
+                T* r = dV + (size_t)(row0 + lane) * p.ld + col_h + dc;
+#pragma unroll
+                for (int t = 0; t < AT_DCH; ++t)
+                    if (t < w) stf<T>(r + t, acc[t]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int check(const AttnParams& p) {
+    MOREC_CHECK_ARG(p.q && p.k && p.v, "attention: null q/k/v");
+    MOREC_CHECK_ARG(p.head_dim % 4 == 0 && p.head_dim > 0, "attention: head_dim=%d must be a multiple of 4", p.head_dim);
+    MOREC_CHECK_ARG(p.seqlen <= AT_MAXL && p.seqlen > 0, "attention: max sequence length %d > %d unsupported", p.seqlen, AT_MAXL);
+    MOREC_CHECK_ARG(p.ld % 4 == 0 && p.ld_o % 4 == 0, "attention: row strides must be multiples of 4");
+    MOREC_CHECK_ARG(!(p.key_mask && p.cu_seqlens), "attention: key_mask requires fixed-length sequences");
+    return MOREC_OK;
+}
+
+}  // namespace morec
+
+using namespace morec;
+
+extern "C" int morec_attn_fwd(const void* q, const void* k, const void* v, void* o, const int32_t* cu_seqlens,
+                              const float* key_mask, int causal, int n_seq, int seqlen, int n_heads, int head_dim,
+                              int ld, int ld_o, float scale, float masked_add, int dtype, float dropout_p, uint64_t seed,
+                              uint64_t offset, void* stream) {
+    AttnParams p{};
+    p.q = q; p.k = k; p.v = v; p.out = o; p.cu_seqlens = cu_seqlens; p.key_mask = key_mask; p.causal = causal;
+    p.n_seq = n_seq; p.seqlen = seqlen; p.n_heads = n_heads; p.head_dim = head_dim; p.ld = ld; p.ld_o = ld_o; p.scale = scale;
+    p.masked_add = masked_add; p.dropout_p = dropout_p; p.seed = seed; p.offset = offset;
+    MOREC_CHECK_ARG(o, "attn_fwd: null output");
+    if (int rc = check(p)) return rc;
+    if (n_seq <= 0) return MOREC_OK;
+    const int pairs = n_seq * n_heads;
+    int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
+    const int cap = num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == 0) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    else attn_fwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_attn_bwd(const void* q, const void* k, const void* v, const void* d_o, void* dq, void* dk,
+                              void* dv, const int32_t* cu_seqlens, const float* key_mask, int causal, int n_seq,
+                              int seqlen, int n_heads, int head_dim, int ld, int ld_o, float scale, float masked_add,
+                              int dtype, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+    AttnParams p{};
+    p.q = q; p.k = k; p.v = v; p.o = d_o; p.dq = dq; p.dk = dk; p.dv = dv; p.cu_seqlens = cu_seqlens;
+    p.key_mask = key_mask; p.causal = causal; p.n_seq = n_seq; p.seqlen = seqlen; p.n_heads = n_heads;
+    p.head_dim = head_dim; p.ld = ld; p.ld_o = ld_o; p.scale = scale; p.masked_add = masked_add; p.dropout_p = dropout_p;
+    p.seed = seed; p.offset = offset;
+    MOREC_CHECK_ARG(d_o && dq && dk && dv, "attn_bwd: null pointer");
+    if (int rc = check(p)) return rc;
+    if (n_seq <= 0) return MOREC_OK;
+    const int pairs = n_seq * n_heads;
+    int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
+    const int cap = num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    constexpr size_t smem = (size_t)AT_WARPS * (AT_MAXL * AT_DCH + 2 * AT_MAXL * 33) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    if (dtype == 0) attn_bwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    else attn_bwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}

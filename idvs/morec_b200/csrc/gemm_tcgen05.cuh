@@ -42,7 +42,7 @@ constexpr int BLOCK_M = 128;
 constexpr int kThreads = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-7 epilogue
 constexpr int kEpiWarps = 4;
 constexpr int kEpiBufBytes = 4096;   // one 32-row x 128B sub-tile (32 fp32 or 64 bf16 columns), SWIZZLE_128B
-constexpr int kEpiBufsPerWarp = 4;
+constexpr int kEpiBufsPerWarp = 4;      // 2 in the 3xTF32 configuration (its doubled stages need the room)
 
 struct TileSched {
     int M, N, K;
@@ -64,16 +64,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// KIND: 0 = fp32 storage, one kind::tf32 pass          ("tf32": ~1e-3 relative, operands truncated to 10 mantissa bits)
+//       1 = bf16 storage, kind::f16
+//       2 = fp32 storage, error-compensated 3xTF32     ("fp32" parity mode): each operand tile is split IN SHARED
+//           MEMORY into hi = tf32-truncated(x) and lo = x - hi by four converter warps, and the tensor core
+//           accumulates hi*hi + hi*lo + lo*hi into the same TMEM accumulator (~2^-21 relative, fp32 grade).
 template <int KIND, int BLOCK_N>
 struct Cfg {
-    static constexpr int ELEM = KIND == 0 ? 4 : 2;
+    static constexpr bool X3 = KIND == 2;
+    static constexpr int ELEM = KIND == 1 ? 2 : 4;
     static constexpr int BLOCK_K = 128 / ELEM;          // K elements per stage (one 128B swizzle row)
     static constexpr int UMMA_K = 32 / ELEM;            // 8 (tf32) / 16 (bf16)
     static constexpr int CHUNK = 128 / ELEM;            // MN elements per 128B row of an MN-major tile
     static constexpr int A_BYTES = BLOCK_M * 128;
     static constexpr int B_BYTES = BLOCK_N * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = kEpiWarps * kEpiBufsPerWarp * kEpiBufBytes;
+    static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;                 // bytes landed by TMA per stage
+    static constexpr int STAGE_BYTES = LOAD_BYTES * (X3 ? 2 : 1);        // x3: [A_hi | B_hi | A_lo | B_lo]
+    static constexpr int THREADS = kThreads + (X3 ? 128 : 0);            // x3: warps 8-11 split the operands
+    static constexpr int EPI_BUFS = X3 ? 2 : kEpiBufsPerWarp;
+    static constexpr int EPI_BYTES = kEpiWarps * EPI_BUFS * kEpiBufBytes;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_LIMIT = 227 * 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES;
@@ -88,16 +97,22 @@ struct Cfg {
 // fp32 output : 32 columns  -> one 128B row, stored immediately.
 // bf16 output : 32 columns  -> half a 128B row; the store is issued after the odd chunk.
 struct EpiStore {
-    uint8_t* bufs;     // this warp's kEpiBufsPerWarp staging buffers
+    uint8_t* bufs;     // this warp's staging buffers
     int buf;           // rotating index
     int lane;
-    __device__ __forceinline__ void begin() {
-        // conservative for two interleaved output streams (C2 and C): two buffers are filled before either commit
-        if (lane == 0) tma_store_wait_read<kEpiBufsPerWarp - 2>();
+    int nbufs;         // 4 (default) or 2 (3xTF32 configuration)
+    // before filling `nslots` buffers, at most nbufs - nslots earlier stores may still be reading theirs
+    __device__ __forceinline__ void begin(int nslots) {
+        if (lane == 0) {
+            const int allow = nbufs - nslots;
+            if (allow >= 2) tma_store_wait_read<2>();
+            else if (allow == 1) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+        }
         __syncwarp();
     }
     __device__ __forceinline__ void put_f32(const float (&x)[32], int slot) {
-        uint8_t* rowp = bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes + lane * 128;
+        uint8_t* rowp = bufs + ((buf + slot) % nbufs) * kEpiBufBytes + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int pj = j ^ (lane & 7);
@@ -105,7 +120,7 @@ struct EpiStore {
         }
     }
     __device__ __forceinline__ void put_bf16(const float (&x)[32], int half, int slot) {
-        uint8_t* rowp = bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes + lane * 128;
+        uint8_t* rowp = bufs + ((buf + slot) % nbufs) * kEpiBufBytes + lane * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int pj = (half * 4 + j) ^ (lane & 7);
@@ -123,13 +138,13 @@ struct EpiStore {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            const uint32_t src = smem_u32(bufs + ((buf + slot) % kEpiBufsPerWarp) * kEpiBufBytes);
+            const uint32_t src = smem_u32(bufs + ((buf + slot) % nbufs) * kEpiBufBytes);
             if (reduce_add) tma_reduce_add_2d(tm, src, col0, row0);
             else tma_store_2d(tm, src, col0, row0);
             tma_store_commit();
         }
     }
-    __device__ __forceinline__ void advance(int n) { buf = (buf + n) % kEpiBufsPerWarp; }
+    __device__ __forceinline__ void advance(int n) { buf = (buf + n) % nbufs; }
     // One 32-column chunk `c` of the tile whose first column is n0.  `slot`/`nslots`: an epilogue with two output
     // streams emits slot 1 (C2) then slot 0 (C) for every chunk; the buffer ring advances once per chunk (fp32) or
     // once per chunk pair (bf16) after the LAST slot has been emitted.
@@ -137,12 +152,12 @@ struct EpiStore {
                                          bool out_bf16, bool reduce_add, int slot = 0, int nslots = 1) {
         const bool first = slot == nslots - 1, last = slot == 0;
         if (!out_bf16) {
-            if (first) begin();
+            if (first) begin(nslots);
             put_f32(x, slot);
             commit(tm, n0 + c * 32, row0, reduce_add, slot);
             if (last) advance(nslots);
         } else {
-            if ((c & 1) == 0 && first) begin();
+            if ((c & 1) == 0 && first) begin(nslots);
             put_bf16(x, c & 1, slot);
             if (c & 1) {
                 commit(tm, n0 + (c - 1) * 32, row0, false, slot);
@@ -159,7 +174,7 @@ struct EpiStore {
 //   taddr already includes the warp's lane quarter and the accumulator stage; thread `lane` owns row m0+q*32+lane.
 
 template <int KIND, int BLOCK_N, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<KIND, BLOCK_N>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TileSched p,
             const typename Epi::Params ep) {
@@ -174,7 +189,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* empty_bar = bars + C::STAGES;           // [STAGES]
     uint64_t* tfull_bar = bars + 2 * C::STAGES;       // [2]
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* conv_bar = bars + 2 * C::STAGES + 4;    // [STAGES] (x3 only): operand split done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -189,6 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&conv_bar[s]), 128);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
@@ -222,7 +239,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
-                    mbar_expect_tx(fb, C::STAGE_BYTES);
+                    mbar_expect_tx(fb, C::LOAD_BYTES);
                     const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
                     const uint32_t sb = sa + C::A_BYTES;
                     const int k0 = kb * C::BLOCK_K;
@@ -248,7 +265,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ================================ MMA issuer ================================
         // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A major [15], B major [16],
         // N>>3 [17,23), M>>4 [24,29)
-        constexpr uint32_t fmt = KIND == 0 ? 2u : 1u;   // tf32 : bf16
+        constexpr uint32_t fmt = KIND == 1 ? 1u : 2u;   // bf16 : tf32
+        constexpr int MK = KIND == 1 ? 1 : 0;           // tc_mma kind
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                                ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -264,7 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                mbar_wait(smem_u32(C::X3 ? &conv_bar[stage] : &full_bar[stage]), phase);
                 tc_fence_after();
                 if (lane == 0) {   // one fixed thread issues every MMA and commit of this CTA
                     const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
@@ -274,13 +292,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         // K-major : 32 bytes per UMMA_K inside the 128B swizzle row; SBO = 8 rows * 128B.
                         // MN-major: UMMA_K k-rows of 128B each; LBO = next 128B chunk along MN, SBO = next 8 k-rows.
                         // (tf32 MN-major uses the 32B-atom swizzle: 4 k-rows per atom -> SBO = 512B, layout type 1.)
-                        constexpr uint32_t mn_sbo = KIND == 0 ? 512 : 1024;
-                        constexpr uint32_t mn_lt = KIND == 0 ? 1 : 2;
+                        constexpr uint32_t mn_sbo = KIND == 1 ? 1024 : 512;
+                        constexpr uint32_t mn_lt = KIND == 1 ? 2 : 1;
                         const uint64_t ad = p.a_mn ? make_smem_desc(sa + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
                                                    : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t bd = p.b_mn ? make_smem_desc(sb + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
                                                    : make_smem_desc(sb + k * 32, 16, 1024);
-                        tc_mma<KIND>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        tc_mma<MK>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if constexpr (C::X3) {
+                            // + hi*lo + lo*hi : the lo tiles sit LOAD_BYTES behind the hi tiles (start address
+                            // field counts 16-byte units)
+                            constexpr uint64_t lo_off = (uint64_t)(C::LOAD_BYTES >> 4);
+                            tc_mma<MK>(d_tmem, ad, bd + lo_off, idesc, 1u);
+                            tc_mma<MK>(d_tmem, ad + lo_off, bd, idesc, 1u);
+                        }
                     }
                     tc_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot when these MMAs retire
                     if (kb == kb1 - 1) tc_commit(smem_u32(&tfull_bar[acc]));   // accumulator complete -> epilogue
@@ -290,11 +315,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4) {
+    } else if (C::X3 && warp >= 8) {
+        // ================================ operand split (3xTF32) ================================
+        const int ct = threadIdx.x - 256;   // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                float4* hi = reinterpret_cast<float4*>(stage_base + stage * C::STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(stage_base + stage * C::STAGE_BYTES + C::LOAD_BYTES);
+#pragma unroll 4
+                for (int i = ct; i < C::LOAD_BYTES / 16; i += 128) {
+                    const float4 x = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(smem_u32(&conv_bar[stage]));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ================================ epilogue ================================
         const int q = warp - 4;  // TMEM lane quarter == warp % 4
         EpiStore st;
-        st.bufs = epi_base + q * (kEpiBufsPerWarp * kEpiBufBytes);
+        st.bufs = epi_base + q * (C::EPI_BUFS * kEpiBufBytes);
+        st.nbufs = C::EPI_BUFS;
         st.buf = 0;
         st.lane = lane;
         int acc = 0;
@@ -333,13 +388,14 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
     using C = Cfg<KIND, BLOCK_N>;
     constexpr int ELEM = C::ELEM;
     const bool bf = KIND == 1;
+    constexpr bool SW32 = KIND != 1;   // MN-major 32-bit operands need the 32B-atom swizzle
     CUtensorMap tmA, tmB, tmC, tmC2;
     int rc;
     if (!g.a_mn) rc = make_tmap_2d(&tmA, g.A, bf, g.K, g.M, (uint64_t)g.lda * ELEM, C::BLOCK_K, BLOCK_M);
-    else         rc = make_tmap_2d(&tmA, g.A, bf, g.M, g.K, (uint64_t)g.lda * ELEM, C::CHUNK, C::BLOCK_K, KIND == 0);
+    else         rc = make_tmap_2d(&tmA, g.A, bf, g.M, g.K, (uint64_t)g.lda * ELEM, C::CHUNK, C::BLOCK_K, SW32);
     if (rc) return rc;
     if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, bf, g.K, g.N, (uint64_t)g.ldb * ELEM, C::BLOCK_K, BLOCK_N);
-    else         rc = make_tmap_2d(&tmB, g.B, bf, g.N, g.K, (uint64_t)g.ldb * ELEM, C::CHUNK, C::BLOCK_K, KIND == 0);
+    else         rc = make_tmap_2d(&tmB, g.B, bf, g.N, g.K, (uint64_t)g.ldb * ELEM, C::CHUNK, C::BLOCK_K, SW32);
     if (rc) return rc;
     const int out_elem = g.out_bf16 ? 2 : 4;
     const int out_cols = 128 / out_elem;
@@ -388,16 +444,20 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
         MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
 
+inline bool gemm_is_wide(int N) { return (N % 256 == 0) || N > 384; }
+inline int gemm_block_n(int N, int dtype) { return dtype == 2 ? 128 : (gemm_is_wide(N) ? 256 : 128); }
+
 template <class Epi>
 int gemm_dispatch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
     MOREC_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-    MOREC_CHECK_ARG(g.dtype == 0 || g.dtype == 1, "gemm: dtype must be 0 (fp32/tf32) or 1 (bf16)");
-    const bool wide = (g.N % 256 == 0) || g.N > 384;
+    MOREC_CHECK_ARG(g.dtype >= 0 && g.dtype <= 2, "gemm: dtype must be 0 (fp32/tf32), 1 (bf16) or 2 (fp32/3xtf32)");
+    const bool wide = gemm_is_wide(g.N);
+    if (g.dtype == 2) return gemm_launch<2, 128, Epi>(g, ep, stream);   // doubled stages: 128-wide tiles only
     if (g.dtype == 0) return wide ? gemm_launch<0, 256, Epi>(g, ep, stream) : gemm_launch<0, 128, Epi>(g, ep, stream);
     return wide ? gemm_launch<1, 256, Epi>(g, ep, stream) : gemm_launch<1, 128, Epi>(g, ep, stream);
 }

@@ -1,0 +1,331 @@
+// Row-wise gather / scatter / reduction kernels of the MoRec step (all HBM-bound, vectorised, grid-stride).
+//
+//   morec_bert_embed_fwd/bwd   HF BertEmbeddings gathers: word[id] + position[pos] + token_type[0]   (encoders.py:68)
+//   morec_gather_rows          CLS pooling h[:,0] (encoders.py:69), unique-item -> slot expansion, nn.Embedding
+//                              forward of the ID tower (model.py:37), input_embs[:, :-1] slicing (model.py:39-41)
+//   morec_scatter_add_rows     the matching backward (embedding_dense_backward / index_select backward)
+//   morec_colsum               bias gradients
+//   morec_adamw_multi          multi-tensor AdamW with fused grad unscale + found-inf (run.py:159-162, 245-247)
+#include "../../../include/morec_b200.h"
+#include "common.cuh"
+
+namespace morec {
+
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------------------------------------------------------------------------------------- BERT embeddings
+template <typename T>
+__global__ void bert_embed_fwd_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ pos,
+                                      const float* __restrict__ word, const float* __restrict__ posemb,
+                                      const float* __restrict__ type0, T* __restrict__ out, int n_tok, int H) {
+    const int nv = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_tok * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / nv), c = (int)(i - (size_t)t * nv) * 4;
+        const float4 a = *reinterpret_cast<const float4*>(word + (size_t)ids[t] * H + c);
+        const float4 b = *reinterpret_cast<const float4*>(posemb + (size_t)pos[t] * H + c);
+        const float4 d = *reinterpret_cast<const float4*>(type0 + c);
+        st4<T>(out + (size_t)t * H + c, make_float4(a.x + b.x + d.x, a.y + b.y + d.y, a.z + b.z + d.z, a.w + b.w + d.w));
+    }
+}
+
+template <typename T>
+__global__ void bert_embed_bwd_kernel(const T* __restrict__ dz, const int64_t* __restrict__ ids,
+                                      const int32_t* __restrict__ pos, float* __restrict__ dword,
+                                      float* __restrict__ dposemb, int n_tok, int H) {
+    const int nv = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_tok * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / nv), c = (int)(i - (size_t)t * nv) * 4;
+        const float4 g = ld4<T>(dz + (size_t)t * H + c);
+        if (dword) {
+            float* w = dword + (size_t)ids[t] * H + c;
+            atomicAdd(w, g.x); atomicAdd(w + 1, g.y); atomicAdd(w + 2, g.z); atomicAdd(w + 3, g.w);
+        }
+        if (dposemb) {
+            float* q = dposemb + (size_t)pos[t] * H + c;
+            atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- gather / scatter
+template <typename TS, typename TD>
+__global__ void gather_rows_kernel(const TS* __restrict__ src, const int32_t* __restrict__ idx, TD* __restrict__ dst,
+                                   int n, int H, int ld_src, int ld_dst) {
+    const int nv = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nv), c = (int)(i - (size_t)r * nv) * 4;
+        const int s = idx[r];
+        const float4 v = s >= 0 ? ld4<TS>(src + (size_t)s * ld_src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st4<TD>(dst + (size_t)r * ld_dst + c, v);
+    }
+}
+
+template <typename TS>
+__global__ void scatter_add_rows_kernel(const TS* __restrict__ src, const int32_t* __restrict__ idx,
+                                        float* __restrict__ dst, int n, int H, int ld_src, int ld_dst) {
+    const int nv = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nv), c = (int)(i - (size_t)r * nv) * 4;
+        const int d = idx[r];
+        if (d < 0) continue;
+        const float4 v = ld4<TS>(src + (size_t)r * ld_src + c);
+        float* o = dst + (size_t)d * ld_dst + c;
+        atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- column sum
+// out[n] += sum_m x[m, n]; CTA = 32 x 8 threads: each thread owns 4 columns, 8 row groups; grid-stride over rows.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
+                                                     int ld, int rows_per_cta) {
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 4;
+    const int r0 = blockIdx.y * rows_per_cta;
+    const int r1 = min(M, r0 + rows_per_cta);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < N) {
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const float4 v = ld4<T>(x + (size_t)r * ld + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < N) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { acc.x += red[k][tx].x; acc.y += red[k][tx].y; acc.z += red[k][tx].z; acc.w += red[k][tx].w; }
+        atomicAdd(out + c, acc.x); atomicAdd(out + c + 1, acc.y); atomicAdd(out + c + 2, acc.z); atomicAdd(out + c + 3, acc.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- activation bwd
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ aux, T* __restrict__ out, size_t n4,
+                               int mode) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 g = ld4<T>(dy + 4 * i), a = ld4<T>(aux + 4 * i);
+        float4 o;
+        if (mode == 0) {
+            o.x = g.x * gelu_erf_grad(a.x); o.y = g.y * gelu_erf_grad(a.y);
+            o.z = g.z * gelu_erf_grad(a.z); o.w = g.w * gelu_erf_grad(a.w);
+        } else {
+            o.x = a.x > 0.f ? g.x : 0.f; o.y = a.y > 0.f ? g.y : 0.f;
+            o.z = a.z > 0.f ? g.z : 0.f; o.w = a.w > 0.f ? g.w : 0.f;
+        }
+        st4<T>(out + 4 * i, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- casts
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        st4<__nv_bfloat16>(dst + 4 * i, *reinterpret_cast<const float4*>(src + 4 * i));
+}
+
+// ---------------------------------------------------------------------------------------------- AdamW (multi-tensor)
+struct AdamChunk {
+    float* p; const float* g; float* m; float* v; __nv_bfloat16* p_bf16;
+    int n; float lr, wd;
+};
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamChunk* __restrict__ chunks, int n_chunks,
+                                                          float beta1, float beta2, float eps, float bc1, float bc2,
+                                                          const float* __restrict__ inv_scale,
+                                                          const float* __restrict__ found_inf) {
+    // found_inf != 0 -> skip the whole step (GradScaler semantics)
+    if (found_inf && *found_inf != 0.f) return;
+    const float gs = inv_scale ? *inv_scale : 1.f;
+    for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+        const AdamChunk ch = chunks[ci];
+        for (int i = threadIdx.x * 4; i < ch.n; i += blockDim.x * 4) {
+            if (i + 4 <= ch.n) {
+                float4 p = *reinterpret_cast<float4*>(ch.p + i);
+                float4 g = *reinterpret_cast<const float4*>(ch.g + i);
+                float4 m = *reinterpret_cast<float4*>(ch.m + i);
+                float4 v = *reinterpret_cast<float4*>(ch.v + i);
+                float* pp = &p.x; float* gp = &g.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float gg = gp[k] * gs;
+                    pp[k] *= (1.f - ch.lr * ch.wd);
+                    mp[k] = beta1 * mp[k] + (1.f - beta1) * gg;
+                    vp[k] = beta2 * vp[k] + (1.f - beta2) * gg * gg;
+                    const float denom = sqrtf(vp[k]) / sqrtf(bc2) + eps;
+                    pp[k] -= (ch.lr / bc1) * (mp[k] / denom);
+                }
+                *reinterpret_cast<float4*>(ch.p + i) = p;
+                *reinterpret_cast<float4*>(ch.m + i) = m;
+                *reinterpret_cast<float4*>(ch.v + i) = v;
+                if (ch.p_bf16) st4<__nv_bfloat16>(ch.p_bf16 + i, p);
+            } else {
+                for (int k = i; k < ch.n; ++k) {
+                    const float gg = ch.g[k] * gs;
+                    float pk = ch.p[k] * (1.f - ch.lr * ch.wd);
+                    const float mk = beta1 * ch.m[k] + (1.f - beta1) * gg;
+                    const float vk = beta2 * ch.v[k] + (1.f - beta2) * gg * gg;
+                    pk -= (ch.lr / bc1) * (mk / (sqrtf(vk) / sqrtf(bc2) + eps));
+                    ch.p[k] = pk; ch.m[k] = mk; ch.v[k] = vk;
+                    if (ch.p_bf16) ch.p_bf16[k] = __float2bfloat16(pk);
+                }
+            }
+        }
+    }
+}
+
+// max |g| finite check over chunks: found_inf = 1 if any grad is inf/nan
+__global__ void __launch_bounds__(256) grad_check_kernel(const AdamChunk* __restrict__ chunks, int n_chunks,
+                                                         float* __restrict__ found_inf) {
+    bool bad = false;
+    for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+        const AdamChunk ch = chunks[ci];
+        for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+            const float g = ch.g[i];
+            bad |= !(fabsf(g) <= 3.0e38f);
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.f;
+}
+
+static int grid_for(size_t work, int threads) {
+    size_t b = (work + threads - 1) / threads;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace morec
+
+using namespace morec;
+
+extern "C" int morec_bert_embed_fwd(const int64_t* ids, const int32_t* pos, const float* word, const float* posemb,
+                                    const float* type0, void* out, int n_tok, int H, int dtype, void* stream) {
+    MOREC_CHECK_ARG(ids && pos && word && posemb && type0 && out, "bert_embed_fwd: null pointer");
+    MOREC_CHECK_ARG(H % 4 == 0, "bert_embed_fwd: H %% 4 != 0");
+    if (n_tok <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n_tok * (H / 4), 256);
+    if (dtype == 0) bert_embed_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(ids, pos, word, posemb, type0, (float*)out, n_tok, H);
+    else bert_embed_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(ids, pos, word, posemb, type0, (__nv_bfloat16*)out, n_tok, H);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_bert_embed_bwd(const void* dz, const int64_t* ids, const int32_t* pos, float* dword,
+                                    float* dposemb, int n_tok, int H, int dtype, void* stream) {
+    MOREC_CHECK_ARG(dz && ids && pos, "bert_embed_bwd: null pointer");
+    if (n_tok <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n_tok * (H / 4), 256);
+    if (dtype == 0) bert_embed_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dz, ids, pos, dword, dposemb, n_tok, H);
+    else bert_embed_bwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, ids, pos, dword, dposemb, n_tok, H);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int H, int ld_src, int ld_dst,
+                                 int src_dtype, int dst_dtype, void* stream) {
+    MOREC_CHECK_ARG(src && idx && dst, "gather_rows: null pointer");
+    MOREC_CHECK_ARG(H % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0, "gather_rows: H/ld must be multiples of 4");
+    if (n <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n * (H / 4), 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == 0 && dst_dtype == 0) gather_rows_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, idx, (float*)dst, n, H, ld_src, ld_dst);
+    else if (src_dtype == 0 && dst_dtype == 1) gather_rows_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
+    else if (src_dtype == 1 && dst_dtype == 1) gather_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
+    else gather_rows_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, n, H, ld_src, ld_dst);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_scatter_add_rows(const void* src, const int32_t* idx, float* dst, int n, int H, int ld_src,
+                                      int ld_dst, int src_dtype, void* stream) {
+    MOREC_CHECK_ARG(src && idx && dst, "scatter_add_rows: null pointer");
+    MOREC_CHECK_ARG(H % 4 == 0 && ld_src % 4 == 0, "scatter_add_rows: H/ld must be multiples of 4");
+    if (n <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n * (H / 4), 256);
+    if (src_dtype == 0) scatter_add_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, idx, dst, n, H, ld_src, ld_dst);
+    else scatter_add_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, idx, dst, n, H, ld_src, ld_dst);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_colsum(const void* x, float* out, int M, int N, int ld, int dtype, void* stream) {
+    MOREC_CHECK_ARG(x && out, "colsum: null pointer");
+    MOREC_CHECK_ARG(N % 4 == 0 && ld % 4 == 0, "colsum: N/ld must be multiples of 4");
+    if (M <= 0) return MOREC_OK;
+    const int gx = (N / 4 + 31) / 32;
+    int gy = (num_sms() * 4 + gx - 1) / gx;
+    int rows_per = (M + gy - 1) / gy;
+    if (rows_per < 64) rows_per = 64;
+    gy = (M + rows_per - 1) / rows_per;
+    dim3 grid(gx, gy);
+    if (dtype == 0) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, out, M, N, ld, rows_per);
+    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, M, N, ld, rows_per);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mode, int dtype, void* stream) {
+    MOREC_CHECK_ARG(dy && aux && out, "act_bwd: null pointer");
+    MOREC_CHECK_ARG(n % 4 == 0, "act_bwd: n %% 4 != 0");
+    if (n <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n / 4, 256);
+    if (dtype == 0) act_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)aux, (float*)out, (size_t)n / 4, mode);
+    else act_bwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, (size_t)n / 4, mode);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    MOREC_CHECK_ARG(src && dst, "cast: null pointer");
+    MOREC_CHECK_ARG(n % 4 == 0, "cast: n %% 4 != 0");
+    if (n <= 0) return MOREC_OK;
+    cast_f32_to_bf16_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (size_t)n / 4);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+// chunks: device array of MorecAdamChunk (see header), built once by the host optimizer wrapper
+extern "C" int morec_adamw_multi(const void* chunks, int n_chunks, float beta1, float beta2, float eps, int step,
+                                 const float* inv_scale, float* found_inf, int check_finite, void* stream) {
+    MOREC_CHECK_ARG(chunks, "adamw_multi: null chunk table");
+    static_assert(sizeof(AdamChunk) == sizeof(MorecAdamChunk), "ABI struct mismatch");
+    if (n_chunks <= 0) return MOREC_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    const int grid = n_chunks < num_sms() * 8 ? n_chunks : num_sms() * 8;
+    if (check_finite && found_inf) {
+        grad_check_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, n_chunks, found_inf);
+        MOREC_LAUNCH_CHECK();
+    }
+    adamw_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, n_chunks, beta1, beta2, eps, bc1,
+                                                              bc2, inv_scale, found_inf);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}

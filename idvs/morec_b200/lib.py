@@ -54,6 +54,34 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# fp32-storage GEMM precision: True -> error-compensated 3xTF32 ("fp32" parity mode, C-ABI dtype 2),
+# False -> one TF32 pass ("tf32" mode, dtype 0).  A plain module global (the autograd engine runs backward on its
+# own thread), set by the ops Functions from their saved meta through `fp32_mode`.
+_FP32_X3 = True
+
+
+class fp32_mode:
+    def __init__(self, x3: bool):
+        self.x3 = bool(x3)
+
+    def __enter__(self):
+        global _FP32_X3
+        self.prev = _FP32_X3
+        _FP32_X3 = self.x3
+
+    def __exit__(self, *a):
+        global _FP32_X3
+        _FP32_X3 = self.prev
+
+
+def gemm_dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 2 if _FP32_X3 else 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise MorecError(f"unsupported dtype {t.dtype}")
+
+
 # enum mirrors
 EPI_LINEAR, EPI_GELU, EPI_GELU_NOSAVE, EPI_RELU, EPI_MUL_GELU_GRAD, EPI_MUL_RELU_GRAD = range(6)
 DT_F32, DT_BF16 = 0, 1
@@ -71,8 +99,8 @@ def gemm(A, B, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, ldaux
          epilogue=EPI_LINEAR, alpha=1.0, accumulate=False):
     """Raw morec_gemm.  A/B dtype decides the math kind; C dtype decides the output element type."""
     lib = load()
-    dt = dtype_code(A)
-    assert dtype_code(B) == dt
+    dt = gemm_dtype_code(A)
+    assert gemm_dtype_code(B) == dt
     out_bf16 = 1 if C.dtype == torch.bfloat16 else 0
     rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), c_int(M), c_int(N), c_int(K),
                         c_int(lda), c_int(ldb), c_int(ldc), c_int(ldaux), c_int(int(a_mn)), c_int(int(b_mn)),
@@ -91,14 +119,16 @@ def linear_fwd(x, w, bias=None, *, epilogue=EPI_LINEAR, out=None, pre=None, out_
     return out
 
 
-def linear_dgrad(dy, w, *, epilogue=EPI_LINEAR, aux=None, out=None, out_dtype=None):
-    """dx[M,K] = (dy[M,N] @ w[N,K]) (* act'(aux))."""
+def linear_dgrad(dy, w, *, epilogue=EPI_LINEAR, aux=None, out=None, out_dtype=None, accumulate=False):
+    """dx[M,K] = (dy[M,N] @ w[N,K]) (* act'(aux));  accumulate=True: out (fp32) += dy @ w via TMA reduce-add."""
     M, N = dy.shape
     K = w.shape[1]
     if out is None:
+        assert not accumulate
         out = torch.empty(M, K, device=dy.device, dtype=out_dtype or dy.dtype)
     gemm(dy, w, out, aux=aux, M=M, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldc=out.stride(0),
-         ldaux=(aux.stride(0) if aux is not None else 0), a_mn=False, b_mn=True, epilogue=epilogue)
+         ldaux=(aux.stride(0) if aux is not None else 0), a_mn=False, b_mn=True, epilogue=epilogue,
+         accumulate=accumulate)
     return out
 
 
@@ -110,3 +140,172 @@ def linear_wgrad(dy, x, dw):
     gemm(dy, x, dw, M=N, N=K, K=M, lda=dy.stride(0), ldb=x.stride(0), ldc=dw.stride(0), a_mn=True, b_mn=True,
          accumulate=True)
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers over the remaining entry points (device tensors in, pre-allocated outputs)
+# ------------------------------------------------------------------------------------------------
+def _u64(x):
+    return c_uint64(int(x) & 0xFFFFFFFFFFFFFFFF)
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, residual=None, pos=None, pos_period=0, p_pre=0.0, p_post=0.0, seed=0,
+                  off_pre=0, off_post=0, out=None):
+    """returns (y, y_pre_or_None, rstd)"""
+    M, H = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    y_pre = torch.empty_like(x) if p_post > 0 else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    rc = load().morec_layernorm_fwd(_ptr(x), _ptr(residual), _ptr(pos), c_int(pos_period), _ptr(gamma), _ptr(beta),
+                                    _ptr(y), _ptr(y_pre), _ptr(rstd), c_int(M), c_int(H), c_float(eps),
+                                    c_int(dtype_code(x)), c_float(p_pre), c_float(p_post), _u64(seed), _u64(off_pre),
+                                    _u64(off_post), _stream())
+    _check(rc, "morec_layernorm_fwd")
+    return y, y_pre, rstd
+
+
+def layernorm_bwd(dy, y, gamma, beta, rstd, *, dy2=None, dgamma, dbeta, dbias=None, dpos=None, pos_period=0,
+                  p_pre=0.0, p_post=0.0, seed=0, off_pre=0, off_post=0):
+    """returns (dz, dx_branch) ; dx_branch is dz itself when p_pre == 0"""
+    M, H = dy.shape
+    dz = torch.empty_like(dy)
+    dxb = torch.empty_like(dy) if p_pre > 0 else None
+    rc = load().morec_layernorm_bwd(_ptr(dy), _ptr(dy2), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(rstd), _ptr(dz),
+                                    _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(dpos), c_int(pos_period),
+                                    c_int(M), c_int(H), c_int(dtype_code(dy)), c_float(p_pre), c_float(p_post),
+                                    _u64(seed), _u64(off_pre), _u64(off_post), _stream())
+    _check(rc, "morec_layernorm_bwd")
+    return dz, (dxb if dxb is not None else dz)
+
+
+def attn_fwd(q, k, v, o, *, cu_seqlens=None, key_mask=None, causal=False, n_seq, seqlen, n_heads, head_dim, scale,
+             masked_add=-1e9, dropout_p=0.0, seed=0, offset=0):
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    rc = load().morec_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(key_mask), c_int(int(causal)),
+                               c_int(n_seq), c_int(seqlen), c_int(n_heads), c_int(head_dim), c_int(q.stride(0)),
+                               c_int(o.stride(0)), c_float(scale), c_float(masked_add), c_int(dtype_code(q)), c_float(dropout_p), _u64(seed),
+                               _u64(offset), _stream())
+    _check(rc, "morec_attn_fwd")
+    return o
+
+
+def attn_bwd(q, k, v, do, dq, dk, dv, *, cu_seqlens=None, key_mask=None, causal=False, n_seq, seqlen, n_heads,
+             head_dim, scale, masked_add=-1e9, dropout_p=0.0, seed=0, offset=0):
+    assert q.stride(0) == k.stride(0) == v.stride(0) == dq.stride(0) == dk.stride(0) == dv.stride(0)
+    rc = load().morec_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(cu_seqlens),
+                               _ptr(key_mask), c_int(int(causal)), c_int(n_seq), c_int(seqlen), c_int(n_heads),
+                               c_int(head_dim), c_int(q.stride(0)), c_int(do.stride(0)), c_float(scale), c_float(masked_add),
+                               c_int(dtype_code(q)), c_float(dropout_p), _u64(seed), _u64(offset), _stream())
+    _check(rc, "morec_attn_bwd")
+
+
+def inbatch_mask(row_ids, col_ids, B, L):
+    C = col_ids.numel()
+    Wc = (C + 31) // 32
+    member = torch.empty(B, Wc, device=row_ids.device, dtype=torch.int32)
+    pad = torch.empty(Wc, device=row_ids.device, dtype=torch.int32)
+    rc = load().morec_inbatch_mask(_ptr(row_ids), _ptr(col_ids), _ptr(member), _ptr(pad), c_int(B), c_int(L), c_int(C),
+                                   _stream())
+    _check(rc, "morec_inbatch_mask")
+    return member, pad
+
+
+def inbatch_ce_fwd(P, E, member, pad, log_pop, log_mask, B, L, col_offset=0, want_loss=True):
+    R, D = P.shape
+    C = E.shape[0]
+    NT = load().morec_inbatch_ce_num_tiles(c_int(C), c_int(gemm_dtype_code(P)))
+    dev = P.device
+    part = torch.empty(2, R, NT, device=dev, dtype=torch.float32)
+    tgt = torch.empty(R, device=dev, dtype=torch.float32)
+    row_lse = torch.empty(R, device=dev, dtype=torch.float32)
+    row_loss = torch.empty(R, device=dev, dtype=torch.float32)
+    sum_cnt = torch.empty(2, device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32) if want_loss else None
+    rc = load().morec_inbatch_ce_fwd(_ptr(P), _ptr(E), _ptr(member), _ptr(pad), _ptr(log_pop), _ptr(log_mask), c_int(B),
+                                     c_int(L), c_int(D), c_int(C), c_int(col_offset), c_int(gemm_dtype_code(P)),
+                                     _ptr(part[0]), _ptr(part[1]), _ptr(tgt), _ptr(row_lse), _ptr(row_loss),
+                                     _ptr(sum_cnt), _ptr(loss), _stream())
+    _check(rc, "morec_inbatch_ce_fwd")
+    return loss, row_lse, row_loss, sum_cnt, tgt
+
+
+def inbatch_ce_dlogits(P, E, member, pad, log_pop, log_mask, row_lse, grad_out, n_valid, B, L, col_offset=0):
+    R, D = P.shape
+    C = E.shape[0]
+    align = 4 if P.dtype == torch.float32 else 8
+    ld = (C + align - 1) // align * align
+    dS = torch.empty(R, ld, device=P.device, dtype=P.dtype)
+    rc = load().morec_inbatch_ce_dlogits(_ptr(P), _ptr(E), _ptr(member), _ptr(pad), _ptr(log_pop), _ptr(log_mask),
+                                         _ptr(row_lse), _ptr(grad_out), _ptr(n_valid), c_int(B), c_int(L), c_int(D),
+                                         c_int(C), c_int(col_offset), c_int(gemm_dtype_code(P)), _ptr(dS), c_int(ld), _stream())
+    _check(rc, "morec_inbatch_ce_dlogits")
+    return dS[:, :C]
+
+
+def bert_embed_fwd(ids, pos, word, posemb, type0, out):
+    n_tok, H = out.shape
+    rc = load().morec_bert_embed_fwd(_ptr(ids), _ptr(pos), _ptr(word), _ptr(posemb), _ptr(type0), _ptr(out), c_int(n_tok),
+                                     c_int(H), c_int(dtype_code(out)), _stream())
+    _check(rc, "morec_bert_embed_fwd")
+    return out
+
+
+def bert_embed_bwd(dz, ids, pos, dword, dposemb):
+    n_tok, H = dz.shape
+    rc = load().morec_bert_embed_bwd(_ptr(dz), _ptr(ids), _ptr(pos), _ptr(dword), _ptr(dposemb), c_int(n_tok), c_int(H),
+                                     c_int(dtype_code(dz)), _stream())
+    _check(rc, "morec_bert_embed_bwd")
+
+
+def gather_rows(src, idx, out=None, out_dtype=None):
+    n = idx.numel()
+    H = src.shape[1]
+    if out is None:
+        out = torch.empty(n, H, device=src.device, dtype=out_dtype or src.dtype)
+    rc = load().morec_gather_rows(_ptr(src), _ptr(idx), _ptr(out), c_int(n), c_int(H), c_int(src.stride(0)),
+                                  c_int(out.stride(0)), c_int(dtype_code(src)), c_int(dtype_code(out)), _stream())
+    _check(rc, "morec_gather_rows")
+    return out
+
+
+def scatter_add_rows(src, idx, dst):
+    n, H = src.shape
+    assert dst.dtype == torch.float32
+    rc = load().morec_scatter_add_rows(_ptr(src), _ptr(idx), _ptr(dst), c_int(n), c_int(H), c_int(src.stride(0)),
+                                       c_int(dst.stride(0)), c_int(dtype_code(src)), _stream())
+    _check(rc, "morec_scatter_add_rows")
+    return dst
+
+
+def colsum(x, out):
+    M, N = x.shape
+    rc = load().morec_colsum(_ptr(x), _ptr(out), c_int(M), c_int(N), c_int(x.stride(0)), c_int(dtype_code(x)), _stream())
+    _check(rc, "morec_colsum")
+    return out
+
+
+def act_bwd(dy, aux, mode, out=None):
+    """out = dy * act'(aux); mode 0: erf-GELU (aux = pre-activation), 1: ReLU (aux = activation output)"""
+    out = out if out is not None else torch.empty_like(dy)
+    assert dy.is_contiguous() and aux.is_contiguous()
+    rc = load().morec_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), c_int64(dy.numel()), c_int(mode), c_int(dtype_code(dy)),
+                              _stream())
+    _check(rc, "morec_act_bwd")
+    return out
+
+
+def cast_f32_to_bf16(src, dst):
+    rc = load().morec_cast_f32_to_bf16(_ptr(src), _ptr(dst), c_int64(src.numel()), _stream())
+    _check(rc, "morec_cast_f32_to_bf16")
+    return dst
+
+
+class AdamChunk(ctypes.Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p_bf16", c_void_p),
+                ("n", c_int), ("lr", c_float), ("wd", c_float)]
+
+
+def adamw_multi(chunks_dev, n_chunks, beta1, beta2, eps, step, inv_scale=None, found_inf=None, check_finite=False):
+    rc = load().morec_adamw_multi(_ptr(chunks_dev), c_int(n_chunks), c_float(beta1), c_float(beta2), c_float(eps),
+                                  c_int(step), _ptr(inv_scale), _ptr(found_inf), c_int(int(check_finite)), _stream())
+    _check(rc, "morec_adamw_multi")

@@ -1,0 +1,143 @@
+"""User / item encoders, mirroring inbatch_sasrec_e2e_text/model/encoders.py on the morec_b200 CUDA kernels."""
+import itertools
+
+import torch
+import torch.nn as nn
+from torch.nn.init import xavier_normal_, constant_
+
+from .. import ops
+from .modules import TransformerEncoder
+
+_call_counter = itertools.count(1)
+
+
+def _drop_ctx(training, p_hidden, p_attn):
+    if not training or (p_hidden <= 0 and p_attn <= 0):
+        return ops.DropCtx()
+    return ops.DropCtx(p_hidden=float(p_hidden), p_attn=float(p_attn), seed=int(torch.initial_seed()),
+                       base=next(_call_counter) << 44)
+
+
+def _adt(module):
+    """activation storage dtype of a compute mode: 'fp32' (3xTF32 parity) and 'tf32' store fp32, 'bf16' stores bf16"""
+    return torch.bfloat16 if getattr(module, "compute_dtype", "fp32") == "bf16" else torch.float32
+
+
+def _x3(module):
+    return getattr(module, "compute_dtype", "fp32") == "fp32"
+
+
+class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
+    def __init__(self, item_num, max_seq_len, item_dim, num_attention_heads, dropout, n_layers):
+        super().__init__()
+        self.transformer_encoder = TransformerEncoder(n_vocab=item_num, n_position=max_seq_len, d_model=item_dim,
+                                                      n_heads=num_attention_heads, dropout=dropout, n_layers=n_layers)
+        self.apply(self._init_weights)
+        self.compute_dtype = "fp32"
+
+    def _init_weights(self, module):                # reference: encoders.py:14-21
+        if isinstance(module, nn.Embedding):
+            xavier_normal_(module.weight.data)
+        elif isinstance(module, nn.Linear):
+            xavier_normal_(module.weight.data)
+            if module.bias is not None:
+                constant_(module.bias.data, 0)
+
+    def forward(self, input_embs, log_mask, local_rank=None):
+        """input_embs [B, L, D], log_mask [B, L] -> [B, L, D]   (reference: encoders.py:23-28; also the eval entry
+        data_utils/metrics.py:95)."""
+        te = self.transformer_encoder
+        B, L, D = input_embs.shape
+        adt = _adt(self)
+        drop = _drop_ctx(self.training, te.dropout_p, te.dropout_p)
+        meta = dict(n_blocks=len(te.transformer_blocks), n_heads=te.n_heads, L=L, adt=adt, drop=drop, x3=_x3(self))
+        X = input_embs.reshape(B * L, D)
+        if X.dtype != adt:
+            X = X.to(adt)
+        lm = log_mask.to(torch.float32).contiguous()
+        out = ops.SasrecFn.apply(meta, X, lm, *te.flat_params())
+        return out.view(B, L, D)
+
+
+class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-70
+    """GELU(fc(BertModel(ids, mask)[0][:, 0])).  `bert_model` is the caller's HF BertModel: it is kept as a
+    sub-module (parameter objects, order and names unchanged: run.py:73-75,155,165 address them), but its forward is
+    never called -- the encoder runs on packed tokens in ops.BertTowerFn."""
+
+    def __init__(self, bert_model, item_embedding_dim, word_embedding_dim):
+        super().__init__()
+        self.bert_model = bert_model
+        self.fc = nn.Linear(word_embedding_dim, item_embedding_dim)
+        self.compute_dtype = "fp32"
+
+    def _flat_params(self):
+        bm = self.bert_model
+        e = bm.embeddings
+        ps = [e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight,
+              e.LayerNorm.weight, e.LayerNorm.bias]
+        for lyr in bm.encoder.layer:
+            a, so = lyr.attention.self, lyr.attention.output
+            ps += [a.query.weight, a.query.bias, a.key.weight, a.key.bias, a.value.weight, a.value.bias,
+                   so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+                   lyr.intermediate.dense.weight, lyr.intermediate.dense.bias,
+                   lyr.output.dense.weight, lyr.output.dense.bias, lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias]
+        ps += [self.fc.weight, self.fc.bias]
+        return ps
+
+    def forward(self, text):
+        """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0."""
+        n, two_t = text.shape
+        T = two_t // 2
+        cfg = self.bert_model.config
+        ids = text[:, :T]
+        am = text[:, T:] != 0
+        lens = am.sum(dim=1)
+        keep = lens > 0
+        adt = _adt(self)
+        D = self.fc.weight.shape[0]
+        n_enc = int(keep.sum())                     # one D2H sync per call (sizes of the packed buffers)
+        if n_enc == 0:
+            return torch.zeros(n, D, device=text.device, dtype=adt)
+        enc_rows = torch.nonzero(keep).squeeze(1)
+        am_e = am[enc_rows]
+        ids_e = ids[enc_rows]
+        lens_e = lens[enc_rows]
+        cu = torch.zeros(n_enc + 1, device=text.device, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens_e, 0).to(torch.int32)
+        tok_ids = ids_e[am_e].to(torch.int64).contiguous()
+        tok_pos = torch.arange(T, device=text.device, dtype=torch.int32).view(1, T).expand(n_enc, T)[am_e].contiguous()
+        cls_rows = cu[:-1].contiguous()
+        drop = _drop_ctx(self.training, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
+        meta = dict(n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps, max_len=T,
+                    adt=adt, drop=drop, x3=_x3(self))
+        E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *self._flat_params())
+        if n_enc == n:
+            return E
+        slot2enc = torch.full((n,), -1, device=text.device, dtype=torch.int32)
+        slot2enc[enc_rows] = torch.arange(n_enc, device=text.device, dtype=torch.int32)
+        return ops.GatherRowsFn.apply(E, slot2enc, adt)
+
+
+class Bert_Encoder(torch.nn.Module):                # reference: encoders.py:73-117
+    def __init__(self, args, bert_model):
+        super().__init__()
+        self.args = args
+        self.attributes2length = {'title': args.num_words_title * 2, 'abstract': args.num_words_abstract * 2,
+                                  'body': args.num_words_body * 2}
+        for key in list(self.attributes2length.keys()):
+            if key not in args.news_attributes:
+                self.attributes2length[key] = 0
+        keys = list(self.attributes2length.keys())
+        self.attributes2start = {key: sum(self.attributes2length[k] for k in keys[:keys.index(key)]) for key in keys}
+        assert len(args.news_attributes) > 0
+        if 'opt' in args.bert_model_load:
+            raise NotImplementedError("OPT mean-pooling text tower is outside the hot path (SURVEY.md §2.1 row 1)")
+        self.text_encoders = nn.ModuleDict({'title': Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
+        self.newsname = [name for name in set(args.news_attributes) & {'title', 'abstract', 'body'}]
+
+    def forward(self, news):
+        vecs = [self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]))
+                for name in self.newsname]
+        if len(vecs) == 1:
+            return vecs[0]
+        return torch.mean(torch.stack(vecs, dim=1), dim=1)

@@ -1,0 +1,425 @@
+"""Host-side sequencing of the morec_b200 kernels as torch.autograd Functions.
+
+torch is plumbing here (device memory, streams, the autograd graph between the coarse Functions); every FLOP of the
+hot path runs in the hand-written sm_100a kernels behind the C ABI (idvs/morec_b200/lib.py).  Each Function mirrors
+one piece of the reference's Model.forward (inbatch_sasrec_e2e_text/model/model.py:31-69):
+
+    BertTowerFn   model/encoders.py:63-70  HF BertModel(ids, mask)[0][:, 0] -> fc -> GELU       (packed tokens)
+    GatherRowsFn  model/model.py:37-41     nn.Embedding / slot expansion / input_embs[:, :-1]
+    SasrecFn      model/encoders.py:23-28 + model/modules.py:89-96                               (post-LN blocks)
+    InbatchCEFn   model/model.py:45-67     scoring + debias + masks + CE
+
+Gradients of parameters are produced in fp32 and returned through autograd, so DistributedDataParallel hooks and
+torch.cuda.amp.GradScaler (run.py:148, 245-247) keep working unchanged.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib
+
+_MASKED_ADD = -1e9
+
+
+@dataclass
+class DropCtx:
+    """dropout configuration of one Function call: probabilities + Philox seed + a base offset unique to the call"""
+    p_hidden: float = 0.0
+    p_attn: float = 0.0
+    seed: int = 0
+    base: int = 0
+
+    def off(self, site: int) -> int:
+        return self.base + (site << 36)
+
+
+def _cw(p: torch.Tensor, adt: torch.dtype) -> torch.Tensor:
+    """weight in compute dtype (fp32 params are used in place; bf16 mode makes a shadow copy)"""
+    p = p.detach()
+    if adt == torch.float32:
+        return p
+    sh = torch.empty(p.shape, device=p.device, dtype=torch.bfloat16)
+    if p.numel() % 4 == 0 and p.is_contiguous():
+        lib.cast_f32_to_bf16(p, sh)
+    else:
+        sh.copy_(p)
+    return sh
+
+
+def _with_prec(fn):
+    """run a Function.forward/backward under the fp32 GEMM precision recorded in its meta (see lib.fp32_mode)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        meta = args[0] if isinstance(args[0], dict) else getattr(ctx, "meta", None)
+        x3 = True if meta is None else bool(meta.get("x3", True))
+        with lib.fp32_mode(x3):
+            return fn(ctx, *args)
+    return wrapper
+
+
+def _z32(p):
+    return torch.zeros(p.shape, device=p.device, dtype=torch.float32)
+
+
+def _dgrad_acc(dy, w, into):
+    """into += dy @ w"""
+    if into.dtype == torch.float32:
+        lib.linear_dgrad(dy, w, out=into, accumulate=True)
+    else:
+        into.add_(lib.linear_dgrad(dy, w))
+    return into
+
+
+# ==================================================================================================
+# BERT text tower
+# ==================================================================================================
+class BertTowerFn(torch.autograd.Function):
+    """E[n_seq, D] = GELU(fc(BERT(tokens)[CLS])) over PACKED tokens (pad tokens and pad items are never computed).
+
+    params (flat): word, pos, type, emb_ln_w, emb_ln_b,
+        per layer: q_w,q_b,k_w,k_b,v_w,v_b, ao_w,ao_b, ln1_w,ln1_b, i_w,i_b, o_w,o_b, ln2_w,ln2_b,   then fc_w, fc_b.
+    meta: n_layers, n_heads, eps, max_len, adt (activation dtype), drop (DropCtx)
+    """
+
+    @staticmethod
+    @_with_prec
+    def forward(ctx, meta, tok_ids, tok_pos, cu_seqlens, cls_rows, *params):
+        n_layers, n_heads, eps, max_len, adt, drop = (meta["n_layers"], meta["n_heads"], meta["eps"], meta["max_len"],
+                                                      meta["adt"], meta["drop"])
+        word, posw, typew, eg, eb = params[:5]
+        fc_w, fc_b = params[-2:]
+        H = word.shape[1]
+        n_tok = tok_ids.numel()
+        n_seq = cu_seqlens.numel() - 1
+        dh = H // n_heads
+        dev = word.device
+        scale = 1.0 / math.sqrt(dh)
+        # ---- embeddings: gather + LN (+ dropout after LN: HF BertEmbeddings)
+        z = torch.empty(n_tok, H, device=dev, dtype=adt)
+        lib.bert_embed_fwd(tok_ids, tok_pos, word.detach(), posw.detach(), typew.detach()[0].contiguous(), z)
+        x, x_pre, rstd0 = lib.layernorm_fwd(z, eg.detach(), eb.detach(), eps, p_post=drop.p_hidden, seed=drop.seed,
+                                            off_post=drop.off(0))
+        emb_saved = (x_pre if x_pre is not None else x, rstd0)
+        del z
+        layers = []
+        for l in range(n_layers):
+            (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
+            wqkv = _cw(torch.cat([qw.detach(), kw.detach(), vw.detach()], dim=0), adt)
+            bqkv = torch.cat([qb.detach(), kb.detach(), vb.detach()], dim=0)
+            qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
+            ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
+            lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq,
+                         seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn,
+                         seed=drop.seed, offset=drop.off(1 + 4 * l))
+            ao = lib.linear_fwd(ctxo, _cw(aow, adt), aob.detach())
+            x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+            del ao
+            pre = torch.empty(n_tok, iw.shape[0], device=dev, dtype=adt)
+            act = lib.linear_fwd(x1, _cw(iw, adt), ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
+            fo = lib.linear_fwd(act, _cw(ow, adt), ob.detach())
+            x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+            del fo
+            layers.append([x, qkv, ctxo, x1, rstd1, pre, act, rstd2])
+            x = x2
+        # ---- CLS pooling + fc + GELU
+        cls = lib.gather_rows(x, cls_rows)                                # [n_seq, H]
+        D = fc_w.shape[0]
+        fc_pre = torch.empty(n_seq, D, device=dev, dtype=adt)
+        E = lib.linear_fwd(cls, _cw(fc_w, adt), fc_b.detach(), epilogue=lib.EPI_GELU, pre=fc_pre)
+        ctx.meta = meta
+        ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre)
+        ctx.idx = (tok_ids, tok_pos, cu_seqlens, cls_rows)
+        ctx.params = params
+        return E
+
+    @staticmethod
+    @_with_prec
+    def backward(ctx, dE):
+        meta, saved, params = ctx.meta, ctx.saved, ctx.params
+        tok_ids, tok_pos, cu_seqlens, cls_rows = ctx.idx
+        n_layers, n_heads, eps, max_len, adt, drop = (meta["n_layers"], meta["n_heads"], meta["eps"], meta["max_len"],
+                                                      meta["adt"], meta["drop"])
+        need = [p.requires_grad for p in params]
+        word, posw, typew, eg, eb = params[:5]
+        fc_w, fc_b = params[-2:]
+        H = word.shape[1]
+        n_tok = tok_ids.numel()
+        n_seq = cu_seqlens.numel() - 1
+        dh = H // n_heads
+        dev = word.device
+        scale = 1.0 / math.sqrt(dh)
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        dE = dE.contiguous().to(adt)
+        # ---- fc + GELU backward
+        cls, fc_pre = saved["cls"], saved["fc_pre"]
+        dpre = lib.act_bwd(dE, fc_pre, 0)
+        g_fcw = _z32(fc_w)
+        lib.linear_wgrad(dpre, cls, g_fcw)
+        g_fcb = torch.zeros(fc_w.shape[0], device=dev, dtype=torch.float32)
+        lib.colsum(dpre, g_fcb)
+        grads[-2], grads[-1] = (g_fcw if need[-2] else None), (g_fcb if need[-1] else None)
+        dcls = lib.linear_dgrad(dpre, _cw(fc_w, adt))
+        # ---- scatter CLS grads into the gradient of the last hidden state
+        dx32 = torch.zeros(n_tok, H, device=dev, dtype=torch.float32)
+        lib.scatter_add_rows(dcls, cls_rows, dx32)
+        dx = dx32 if adt == torch.float32 else dx32.to(adt)
+        del dx32
+        x_out = saved["x_last"]
+        for l in reversed(range(n_layers)):
+            (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
+            x, qkv, ctxo, x1, rstd1, pre, act, rstd2 = saved["layers"][l]
+            base = 5 + 16 * l
+            # output LayerNorm (y = x_out)
+            dg2, db2, dob = _z32(g2), _z32(b2), _z32(ob)
+            dz2, dfo = lib.layernorm_bwd(dx, x_out, g2.detach(), b2.detach(), rstd2, dgamma=dg2, dbeta=db2, dbias=dob,
+                                         p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+            del dx
+            # FFN2 / FFN1
+            dow = _z32(ow)
+            lib.linear_wgrad(dfo, act, dow)
+            dpre_i = lib.linear_dgrad(dfo, _cw(ow, adt), epilogue=lib.EPI_MUL_GELU_GRAD, aux=pre)
+            if dfo is not dz2:
+                del dfo
+            dib, diw = _z32(ib), _z32(iw)
+            lib.colsum(dpre_i, dib)
+            lib.linear_wgrad(dpre_i, x1, diw)
+            dx1_b = lib.linear_dgrad(dpre_i, _cw(iw, adt))
+            del dpre_i
+            # attention-output LayerNorm: dy = dz2 + dx1_b, y = x1
+            dg1, db1, daob = _z32(g1), _z32(b1), _z32(aob)
+            dz1, dao = lib.layernorm_bwd(dz2, x1, g1.detach(), b1.detach(), rstd1, dy2=dx1_b, dgamma=dg1, dbeta=db1,
+                                         dbias=daob, p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+            del dz2, dx1_b
+            daow = _z32(aow)
+            lib.linear_wgrad(dao, ctxo, daow)
+            dctx = lib.linear_dgrad(dao, _cw(aow, adt))
+            if dao is not dz1:
+                del dao
+            # attention core
+            dqkv = torch.empty_like(qkv)
+            lib.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+                         cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale,
+                         dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
+            del dctx
+            # fused QKV projection backward
+            wqkv32 = torch.cat([qw.detach(), kw.detach(), vw.detach()], dim=0)
+            dwqkv = torch.zeros_like(wqkv32)
+            lib.linear_wgrad(dqkv, x, dwqkv)
+            dbqkv = torch.zeros(3 * H, device=dev, dtype=torch.float32)
+            lib.colsum(dqkv, dbqkv)
+            dx = _dgrad_acc(dqkv, _cw(wqkv32, adt), dz1)
+            del dqkv, dz1
+            x_out = x
+            lay = (dwqkv[:H], dbqkv[:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:],
+                   daow, daob, dg1, db1, diw, dib, dow, dob, dg2, db2)
+            for j, g in enumerate(lay):
+                grads[base + j] = g if need[base + j] else None
+            saved["layers"][l] = None
+        # ---- embeddings backward: y = dropout(LN(z)), z = word + pos + type
+        y_emb, rstd0 = saved["emb"]
+        deg, deb = _z32(eg), _z32(eb)
+        dtype_sum = torch.zeros(H, device=dev, dtype=torch.float32)
+        dz0, _ = lib.layernorm_bwd(dx, y_emb, eg.detach(), eb.detach(), rstd0, dgamma=deg, dbeta=deb, dbias=dtype_sum,
+                                   p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
+        dword = _z32(word) if need[0] else None
+        dposw = _z32(posw) if need[1] else None
+        if dword is not None or dposw is not None:
+            lib.bert_embed_bwd(dz0, tok_ids, tok_pos, dword, dposw)
+        dtypew = None
+        if need[2]:
+            dtypew = _z32(typew)
+            dtypew[0].copy_(dtype_sum)
+        grads[0], grads[1], grads[2] = dword, dposw, dtypew
+        grads[3] = deg if need[3] else None
+        grads[4] = deb if need[4] else None
+        ctx.saved = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+# ==================================================================================================
+# row gather with index (ID embedding, slot expansion, input slicing)
+# ==================================================================================================
+class GatherRowsFn(torch.autograd.Function):
+    """out[i] = idx[i] >= 0 ? src[idx[i]] : 0 ; backward scatter-adds (fp32 atomics)."""
+
+    @staticmethod
+    def forward(ctx, src, idx, out_dtype):
+        ctx.save_for_backward(idx)
+        ctx.src_shape = src.shape
+        ctx.src_dtype = src.dtype
+        return lib.gather_rows(src.detach(), idx, out_dtype=out_dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        d = torch.zeros(ctx.src_shape, device=dout.device, dtype=torch.float32)
+        lib.scatter_add_rows(dout.contiguous(), idx, d)
+        return (d if ctx.src_dtype == torch.float32 else d.to(ctx.src_dtype)), None, None
+
+
+# ==================================================================================================
+# SASRec user encoder
+# ==================================================================================================
+class SasrecFn(torch.autograd.Function):
+    """H[B*L, D] = TransformerEncoder(X[B*L, D], log_mask[B, L])     (model/modules.py:89-96, post-LN blocks)
+
+    params (flat): pos_emb, ln_w, ln_b, per block: wq, wk, wv, fc, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b
+    meta: n_blocks, n_heads, L, adt, drop (DropCtx: p_hidden = p_attn = drop_rate)
+    """
+
+    @staticmethod
+    @_with_prec
+    def forward(ctx, meta, X, log_mask, *params):
+        n_blocks, n_heads, L, adt, drop = meta["n_blocks"], meta["n_heads"], meta["L"], meta["adt"], meta["drop"]
+        posw, g0, b0 = params[:3]
+        R, D = X.shape
+        B = R // L
+        dk = D // n_heads
+        scale = 1.0 / (dk ** 0.5)
+        dev = X.device
+        X = X.detach().contiguous()
+        h, h_pre, rstd0 = lib.layernorm_fwd(X, g0.detach(), b0.detach(), 1e-6, pos=posw.detach(), pos_period=L,
+                                            p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
+        emb_saved = (h_pre if h_pre is not None else h, rstd0)
+        blocks = []
+        for l in range(n_blocks):
+            (wq, wk, wv, fc, g1, b1, w1, bb1, w2, bb2, g2, b2) = params[3 + 12 * l: 3 + 12 * (l + 1)]
+            wqkv = _cw(torch.cat([wq.detach(), wk.detach(), wv.detach()], dim=0), adt)
+            qkv = lib.linear_fwd(h, wqkv)
+            ctxo = torch.empty(R, D, device=dev, dtype=adt)
+            lib.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ctxo, key_mask=log_mask, causal=True, n_seq=B,
+                         seqlen=L, n_heads=n_heads, head_dim=dk, scale=scale, masked_add=_MASKED_ADD,
+                         dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
+            ao = lib.linear_fwd(ctxo, _cw(fc, adt))
+            h1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), 1e-6, residual=h, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+            u = lib.linear_fwd(h1, _cw(w1, adt), bb1.detach(), epilogue=lib.EPI_RELU)
+            fo = lib.linear_fwd(u, _cw(w2, adt), bb2.detach())
+            h2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), 1e-6, residual=h1, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+            blocks.append([h, qkv, ctxo, h1, rstd1, u, rstd2])
+            h = h2
+        ctx.meta = meta
+        ctx.saved = dict(emb=emb_saved, blocks=blocks, h_last=h, log_mask=log_mask)
+        ctx.params = params
+        return h
+
+    @staticmethod
+    @_with_prec
+    def backward(ctx, dH):
+        meta, saved, params = ctx.meta, ctx.saved, ctx.params
+        n_blocks, n_heads, L, adt, drop = meta["n_blocks"], meta["n_heads"], meta["L"], meta["adt"], meta["drop"]
+        need = [p.requires_grad for p in params]
+        posw, g0, b0 = params[:3]
+        log_mask = saved["log_mask"]
+        dx = dH.contiguous().to(adt)
+        R, D = dx.shape
+        B = R // L
+        dk = D // n_heads
+        scale = 1.0 / (dk ** 0.5)
+        dev = dx.device
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        h_out = saved["h_last"]
+        for l in reversed(range(n_blocks)):
+            (wq, wk, wv, fc, g1, b1, w1, bb1, w2, bb2, g2, b2) = params[3 + 12 * l: 3 + 12 * (l + 1)]
+            h, qkv, ctxo, h1, rstd1, u, rstd2 = saved["blocks"][l]
+            base = 3 + 12 * l
+            dg2, db2, dbb2 = _z32(g2), _z32(b2), _z32(bb2)
+            dz2, dfo = lib.layernorm_bwd(dx, h_out, g2.detach(), b2.detach(), rstd2, dgamma=dg2, dbeta=db2, dbias=dbb2,
+                                         p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+            dw2 = _z32(w2)
+            lib.linear_wgrad(dfo, u, dw2)
+            du = lib.linear_dgrad(dfo, _cw(w2, adt), epilogue=lib.EPI_MUL_RELU_GRAD, aux=u)
+            dbb1, dw1 = _z32(bb1), _z32(w1)
+            lib.colsum(du, dbb1)
+            lib.linear_wgrad(du, h1, dw1)
+            dh1_b = lib.linear_dgrad(du, _cw(w1, adt))
+            dg1, db1 = _z32(g1), _z32(b1)
+            dz1, dao = lib.layernorm_bwd(dz2, h1, g1.detach(), b1.detach(), rstd1, dy2=dh1_b, dgamma=dg1, dbeta=db1,
+                                         p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+            dfc = _z32(fc)
+            lib.linear_wgrad(dao, ctxo, dfc)
+            dctx = lib.linear_dgrad(dao, _cw(fc, adt))
+            dqkv = torch.empty_like(qkv)
+            lib.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                         key_mask=log_mask, causal=True, n_seq=B, seqlen=L, n_heads=n_heads, head_dim=dk, scale=scale,
+                         masked_add=_MASKED_ADD, dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
+            wqkv32 = torch.cat([wq.detach(), wk.detach(), wv.detach()], dim=0)
+            dwqkv = torch.zeros_like(wqkv32)
+            lib.linear_wgrad(dqkv, h, dwqkv)
+            dx = _dgrad_acc(dqkv, _cw(wqkv32, adt), dz1)
+            h_out = h
+            lay = (dwqkv[:D], dwqkv[D:2 * D], dwqkv[2 * D:], dfc, dg1, db1, dw1, dbb1, dw2, dbb2, dg2, db2)
+            for j, g in enumerate(lay):
+                grads[base + j] = g if need[base + j] else None
+            saved["blocks"][l] = None
+        y0, rstd0 = saved["emb"]
+        dg0, db0 = _z32(g0), _z32(b0)
+        dpos = _z32(posw)
+        dX, _ = lib.layernorm_bwd(dx, y0, g0.detach(), b0.detach(), rstd0, dgamma=dg0, dbeta=db0, dpos=dpos,
+                                  pos_period=L, p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
+        # position table may be longer than L rows (it is exactly L in the reference, modules.py:82)
+        grads[0] = dpos if need[0] else None
+        grads[1] = dg0 if need[1] else None
+        grads[2] = db0 if need[2] else None
+        ctx.saved = None
+        return (None, dX, None) + tuple(grads)
+
+
+# ==================================================================================================
+# in-batch debiased cross-entropy
+# ==================================================================================================
+class InbatchCEFn(torch.autograd.Function):
+    """loss = CE over valid rows of  S = P.E^T - log_pop  with the reject mask  (model/model.py:45-67).
+
+    P [B*L, D] (rows of the local users), E [C, D] (all score columns), member/pad from lib.inbatch_mask.
+    Returns (loss, sum_cnt): loss is the local mean; sum_cnt = [sum of valid row losses, n_valid].
+    `n_valid_override` (device scalar) replaces the local count in the backward (global normalisation across ranks).
+    """
+
+    @staticmethod
+    def forward(ctx, meta, P, E, member, pad, log_pop, log_mask, B, L, col_offset, n_valid_override):
+        ctx.meta = meta
+        with lib.fp32_mode(meta.get("x3", True)):
+            return InbatchCEFn._fwd(ctx, P, E, member, pad, log_pop, log_mask, B, L, col_offset, n_valid_override)
+
+    @staticmethod
+    def _fwd(ctx, P, E, member, pad, log_pop, log_mask, B, L, col_offset, n_valid_override):
+        Pc, Ec = P.detach().contiguous(), E.detach().contiguous()
+        loss, row_lse, row_loss, sum_cnt, _ = lib.inbatch_ce_fwd(Pc, Ec, member, pad, log_pop, log_mask, B, L, col_offset)
+        ctx.save_for_backward(Pc, Ec, member, pad, log_pop, log_mask, row_lse, sum_cnt)
+        ctx.dims = (B, L, col_offset)
+        ctx.n_valid_override = n_valid_override
+        ctx.mark_non_differentiable(sum_cnt)
+        return loss, sum_cnt
+
+    @staticmethod
+    def backward(ctx, dloss, _unused):
+        with lib.fp32_mode(ctx.meta.get("x3", True)):
+            return InbatchCEFn._bwd(ctx, dloss)
+
+    @staticmethod
+    def _bwd(ctx, dloss):
+        Pc, Ec, member, pad, log_pop, log_mask, row_lse, sum_cnt = ctx.saved_tensors
+        B, L, col_offset = ctx.dims
+        n_valid = ctx.n_valid_override if ctx.n_valid_override is not None else sum_cnt[1:2]
+        g = dloss.detach().reshape(1).to(torch.float32).contiguous()
+        dS = lib.inbatch_ce_dlogits(Pc, Ec, member, pad, log_pop, log_mask, row_lse, g, n_valid.contiguous(), B, L,
+                                    col_offset)
+        R, D = Pc.shape
+        C = Ec.shape[0]
+        # dP = dS . E      (A = dS [R,C] K-major, B = E stored [C,D] = [K,N] -> MN-major)
+        dP = torch.empty(R, D, device=Pc.device, dtype=Pc.dtype)
+        lib.gemm(dS, Ec, dP, M=R, N=D, K=C, lda=dS.stride(0), ldb=Ec.stride(0), ldc=D, a_mn=False, b_mn=True)
+        # dE = dS^T . P    (A = dS stored [R,C] = [K,M] -> MN-major, B = P stored [R,D] = [K,N] -> MN-major)
+        dE = torch.empty(C, D, device=Pc.device, dtype=Pc.dtype)
+        lib.gemm(dS, Pc, dE, M=C, N=D, K=R, lda=dS.stride(0), ldb=Pc.stride(0), ldc=D, a_mn=True, b_mn=True)
+        return None, dP, dE, None, None, None, None, None, None, None, None

@@ -12,8 +12,11 @@
  *     asynchronous on that stream, re-entrant per stream, and allocate nothing persistent.
  *   - outputs are pre-allocated by the caller.  All matrices are row-major; `ld*` are leading dimensions in
  *     elements.
- *   - dtype: 0 = fp32 storage, tensor-core math in TF32 (tcgen05 kind::tf32), fp32 accumulate  ("parity mode")
- *            1 = bf16 storage, tcgen05 kind::f16, fp32 accumulate                               ("fast mode")
+ *   - dtype (GEMM-bearing calls): 0 = fp32 storage, one tcgen05 kind::tf32 pass, fp32 accumulate     ("tf32")
+ *            1 = bf16 storage, tcgen05 kind::f16, fp32 accumulate                                   ("bf16")
+ *            2 = fp32 storage, error-compensated 3xTF32 on tcgen05 (hi*hi + hi*lo + lo*hi, operands split in
+ *                shared memory), fp32-grade results: the PARITY mode checked against the CPU oracle  ("fp32")
+ *     element-wise / attention / LayerNorm kernels only distinguish the storage type (0 or 2 = fp32, 1 = bf16).
  */
 #ifndef MOREC_B200_H
 #define MOREC_B200_H
@@ -55,6 +58,106 @@ enum {
 int morec_gemm(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M, int N,
                int K, int lda, int ldb, int ldc, int ldaux, int a_mn_major, int b_mn_major, int dtype, int out_bf16,
                int epilogue, float alpha, int accumulate, void* stream);
+
+/* ---- LayerNorm with fused residual / position add and dropout ---------------------------------
+ * forward : z = dropout_pre(x) (+ residual) (+ pos[row % pos_period]);  y_pre = LN(z)*gamma + beta;
+ *           y = dropout_post(y_pre)          rstd[M] saved for the backward; y_pre only needed if p_post > 0
+ *   replaces  LayerNorm(residual + dropout(sublayer(x)))  model/modules.py:16-17,62-63 and HF BertSelfOutput/
+ *             BertOutput;  dropout(LayerNorm(x + position_embedding))  model/modules.py:89-93; HF BertEmbeddings
+ * backward: dy(+dy2) -> dz (grad of z; feeds the residual stream) and dx_branch (= dropout_pre mask applied to
+ *           dz; may be null when p_pre == 0, then dz is also the branch gradient).  `y` is the tensor LN produced
+ *           BEFORE post-dropout (y_pre when p_post > 0).  dgamma/dbeta/dbias/dpos are ACCUMULATED (atomicAdd):
+ *           dbias[H] += colsum(dx_branch) (bias grad of the producing linear), dpos[pos_period,H] += dz rows.
+ * dropout masks are regenerated from (seed, offset) with Philox4x32-10; H % 4 == 0, H <= 2048.
+ */
+int morec_layernorm_fwd(const void* x, const void* residual, const float* pos, int pos_period, const float* gamma,
+                        const float* beta, void* y, void* y_pre, float* rstd, int M, int H, float eps, int dtype,
+                        float p_pre, float p_post, uint64_t seed, uint64_t off_pre, uint64_t off_post, void* stream);
+int morec_layernorm_bwd(const void* dy, const void* dy2, const void* y, const float* gamma, const float* beta,
+                        const float* rstd, void* dz, void* dx_branch, float* dgamma, float* dbeta, float* dbias,
+                        float* dpos, int pos_period, int M, int H, int dtype, float p_pre, float p_post, uint64_t seed,
+                        uint64_t off_pre, uint64_t off_post, void* stream);
+
+/* ---- short-sequence multi-head attention (<= 32 tokens per sequence) ---------------------------
+ * q/k/v (and dq/dk/dv): [n_rows, ld], o (and dO): [n_rows, ld_o], head h in columns [h*head_dim, (h+1)*head_dim).  Sequences are either packed
+ * (cu_seqlens[n_seq+1], rows cu[s]..cu[s+1]) or fixed length `seqlen` (rows s*seqlen..).  Score mask:
+ * causal (k <= q) and/or key_mask[n_seq, seqlen] != 0, applied ADDITIVELY with `masked_add` (-1e9 in the reference,
+ * model/encoders.py:27) so fully-masked rows reproduce the reference's uniform softmax.  Dropout acts on the
+ * probabilities (model/modules.py:30).  head_dim % 4 == 0.
+ *   replaces HF BertSelfAttention (call site model/encoders.py:68) and SelfAttention.forward model/modules.py:27-31
+ */
+int morec_attn_fwd(const void* q, const void* k, const void* v, void* o, const int32_t* cu_seqlens,
+                   const float* key_mask, int causal, int n_seq, int seqlen, int n_heads, int head_dim, int ld,
+                   int ld_o, float scale, float masked_add, int dtype, float dropout_p, uint64_t seed,
+                   uint64_t offset, void* stream);
+int morec_attn_bwd(const void* q, const void* k, const void* v, const void* d_o, void* dq, void* dk, void* dv,
+                   const int32_t* cu_seqlens, const float* key_mask, int causal, int n_seq, int seqlen, int n_heads,
+                   int head_dim, int ld, int ld_o, float scale, float masked_add, int dtype, float dropout_p,
+                   uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- in-batch debiased softmax cross-entropy (model/model.py:45-67) ---------------------------
+ * morec_inbatch_mask   : integer pre-pass.  member[B, ceil(C/32)] bit c = (col_ids[c] in row_ids[b, 0..L]);
+ *                        pad[ceil(C/32)] bit c = (col_ids[c] == 0).  Bit-exact restatement of model.py:51-63.
+ * morec_inbatch_ce_fwd : scoring GEMM P[B*L,D] . E[C,D]^T on tcgen05 with the CE epilogue (logits stay in TMEM):
+ *                        S = P.E^T - log_pop[c]; masked(r,c) = pad(c) | (member(b,c) & c != target(r)) -> -1e4;
+ *                        target(r) = col_offset + b*(L+1) + j + 1.  Workspaces part_m/part_l: [B*L, NT] with
+ *                        NT = morec_inbatch_ce_num_tiles(C).  Outputs row_lse[B*L], row_loss[B*L] (0 for invalid
+ *                        rows), sum_cnt[2] = {sum of valid row losses, number of valid rows}, loss = mean (may be
+ *                        null, e.g. when the caller all-reduces sum_cnt across ranks first).
+ * morec_inbatch_ce_dlogits : dS[B*L, ldds] = (softmax(S) - onehot(target)) * valid(r) * grad_out / n_valid
+ *                        (grad_out, n_valid: device scalars).  dP = dS.E and dE = dS^T.P then run on morec_gemm.
+ */
+int morec_inbatch_mask(const int64_t* row_ids, const int64_t* col_ids, uint32_t* member, uint32_t* pad, int B, int L,
+                       int C, void* stream);
+int morec_inbatch_ce_num_tiles(int C, int dtype);
+int morec_inbatch_ce_fwd(const void* P, const void* E, const uint32_t* member, const uint32_t* pad,
+                         const float* log_pop, const float* log_mask, int B, int L, int D, int C, int col_offset,
+                         int dtype, float* part_m, float* part_l, float* tgt_logit, float* row_lse, float* row_loss,
+                         float* sum_cnt, float* loss, void* stream);
+int morec_inbatch_ce_dlogits(const void* P, const void* E, const uint32_t* member, const uint32_t* pad,
+                             const float* log_pop, const float* log_mask, const float* row_lse, const float* grad_out,
+                             const float* n_valid, int B, int L, int D, int C, int col_offset, int dtype, void* dS,
+                             int ldds, void* stream);
+
+/* ---- row gathers / scatters / reductions ------------------------------------------------------
+ * bert_embed : out[t] = word[ids[t]] + posemb[pos[t]] + type0      (HF BertEmbeddings; LN follows separately)
+ * gather_rows: dst[i] = idx[i] >= 0 ? src[idx[i]] : 0              (CLS pooling encoders.py:69, nn.Embedding
+ *              model.py:37, unique-item -> slot expansion, input_embs[:, :-1] model.py:39-41)
+ * scatter_add_rows: dst[idx[i]] += src[i] (fp32 dst, atomic)        (the matching backward)
+ * colsum     : out[n] += sum_m x[m,n]                               (bias gradients)
+ */
+int morec_bert_embed_fwd(const int64_t* ids, const int32_t* pos, const float* word, const float* posemb,
+                         const float* type0, void* out, int n_tok, int H, int dtype, void* stream);
+int morec_bert_embed_bwd(const void* dz, const int64_t* ids, const int32_t* pos, float* dword, float* dposemb,
+                         int n_tok, int H, int dtype, void* stream);
+int morec_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int H, int ld_src, int ld_dst,
+                      int src_dtype, int dst_dtype, void* stream);
+int morec_scatter_add_rows(const void* src, const int32_t* idx, float* dst, int n, int H, int ld_src, int ld_dst,
+                           int src_dtype, void* stream);
+int morec_colsum(const void* x, float* out, int M, int N, int ld, int dtype, void* stream);
+/* out = dy * act'(aux): mode 0 = erf-GELU with aux = pre-activation (encoders.py:70), 1 = ReLU with aux = output */
+int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mode, int dtype, void* stream);
+int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- multi-tensor AdamW with fused unscale + found-inf (run.py:159-162, 245-247) ---------------
+ * chunks: DEVICE array of MorecAdamChunk (each <= 65536 elements of one parameter).  torch.optim.AdamW
+ * semantics (decoupled weight decay, bias correction with `step` >= 1).  inv_scale (device scalar, may be null)
+ * multiplies the gradients (GradScaler.unscale_); when check_finite != 0 found_inf (device scalar, must be zeroed
+ * by the caller) is set to 1 if any gradient is inf/nan and the whole update is skipped.  p_bf16 (optional)
+ * receives a bf16 copy of the updated parameter (fast-mode weights).
+ */
+typedef struct MorecAdamChunk {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    void* p_bf16;
+    int n;
+    float lr;
+    float wd;
+} MorecAdamChunk;
+int morec_adamw_multi(const void* chunks, int n_chunks, float beta1, float beta2, float eps, int step,
+                      const float* inv_scale, float* found_inf, int check_finite, void* stream);
 
 #ifdef __cplusplus
 }
