@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- training sequences/sec of the MoRec in-batch step (SASRec + BERT-base, L=25) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|tf32|bf16] [--impl morec|reference]
+
+One "step" = one pass of the hot path over one synthetic MIND-shape batch: H2D (e2e only) -> Model.forward (item
+encoder over the batch's items -> SASRec -> in-batch debiased CE) -> backward -> fused AdamW, i.e. the loop body of
+inbatch_sasrec_e2e_text/run.py:231-247.  Workload = BASELINE.json configs[2] (the configuration the metric is
+quoted on): BERT-base, B=64 users per GPU, L=25, T=30 word pieces, D=512, 2 SASRec blocks x 2 heads, N=50k items.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with the W+K batches already resident in HBM;
+`e2e` = the same through the public Model API with host buffers (pinned H2D of each step's batch and a D2H read of
+the loss inside the timed region); `roofline` = the dominant kernel (the tcgen05 GEMM) timed with CUDA events on the
+launching stream inside the timed region; `cpu_baseline` = the oracle port on the host cores on a bounded sample.
+`--impl reference` times the CPU oracle port instead (the reference is Python and cannot travel to the GPU box;
+oracle/morec_oracle.py restates it and is pinned to goldens generated from the unmodified reference).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                 intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                 max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12)
+CFG = dict(B=64, L=25, T=30, D=512, heads=2, blocks=2, N=50000, drop=0.1,
+           lr=1e-4, fine_tune_lr=5e-5, l2=0.01, fine_tune_l2=0.01)      # train_bert_base.py:22-28
+
+
+def make_args(cfg):
+    a = types.SimpleNamespace()
+    a.max_seq_len = cfg["L"]; a.embedding_dim = cfg["D"]; a.num_attention_heads = cfg["heads"]
+    a.drop_rate = cfg["drop"]; a.transformer_block = cfg["blocks"]; a.num_words_title = cfg["T"]
+    a.num_words_abstract = 50; a.num_words_body = 50; a.news_attributes = ["title"]
+    a.bert_model_load = "bert_base_uncased"; a.word_embedding_dim = 768
+    return a
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], 0, set()
+        for (t, line) in self.rows:
+            if t < t0 or t > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_oracle_step_fn(cfg, B_sample, seed):
+    """returns (step_fn, cores): one training step of the oracle port (fwd + bwd + AdamW) on B_sample users"""
+    import torch
+    from transformers import BertConfig, BertModel
+    from oracle import morec_oracle as O
+    from idvs.morec_b200.synth import synth_batch
+    torch.manual_seed(seed)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bert = BertModel(BertConfig(**BERT_BASE))
+    sd = {("bert_encoder.text_encoders.title.bert_model." + k): v for k, v in bert.state_dict().items()}
+    D, L = cfg["D"], cfg["L"]
+    g = torch.Generator().manual_seed(seed)
+    sd["bert_encoder.text_encoders.title.fc.weight"] = torch.randn(D, 768, generator=g) * 0.03
+    sd["bert_encoder.text_encoders.title.fc.bias"] = torch.zeros(D)
+    pre = "user_encoder.transformer_encoder."
+    sd[pre + "position_embedding.weight"] = torch.randn(L, D, generator=g) * 0.05
+    sd[pre + "layer_norm.weight"] = torch.ones(D); sd[pre + "layer_norm.bias"] = torch.zeros(D)
+    for b in range(cfg["blocks"]):
+        q = pre + f"transformer_blocks.{b}."
+        for n in ("w_Q", "w_K", "w_V", "fc"):
+            sd[q + f"multi_head_attention.{n}.weight"] = torch.randn(D, D, generator=g) * 0.04
+        sd[q + "multi_head_attention.layer_norm.weight"] = torch.ones(D); sd[q + "multi_head_attention.layer_norm.bias"] = torch.zeros(D)
+        sd[q + "feed_forward.w_1.weight"] = torch.randn(4 * D, D, generator=g) * 0.03; sd[q + "feed_forward.w_1.bias"] = torch.zeros(4 * D)
+        sd[q + "feed_forward.w_2.weight"] = torch.randn(D, 4 * D, generator=g) * 0.03; sd[q + "feed_forward.w_2.bias"] = torch.zeros(D)
+        sd[q + "feed_forward.layer_norm.weight"] = torch.ones(D); sd[q + "feed_forward.layer_norm.bias"] = torch.zeros(D)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "pooler" not in k) for k, v in sd.items()
+              if v.is_floating_point()}
+    bert_p = [p for k, p in params.items() if "bert_model" in k and p.requires_grad]
+    rec_p = [p for k, p in params.items() if "bert_model" not in k and p.requires_grad]
+    opt = torch.optim.AdamW([{"params": bert_p, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
+                             {"params": rec_p, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+    batch = synth_batch(B_sample, L, cfg["N"], cfg["T"], seed, modal=True)
+
+    def step():
+        opt.zero_grad()
+        out = O.model_forward(params, batch["ids"], batch["items"], batch["log_mask"], batch["pop_prob"], use_modal=True,
+                              n_heads_user=cfg["heads"], n_heads_bert=12)
+        out.loss.backward()
+        opt.step()
+        return float(out.loss)
+
+    return step, cores
+
+
+def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
+    import torch
+    step, cores = cpu_oracle_step_fn(cfg, B_sample, seed)
+    # PyTorch's CPU kernels do not always scale to every core of a big host: calibrate the thread count on one step
+    best = None
+    for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        torch.set_num_threads(nt)
+        t0 = time.time()
+        step()
+        dt = time.time() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    cores = best[1]
+    torch.set_num_threads(cores)
+    for _ in range(max(warmup - 1, 0)):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / max(steps, 1)
+    return dict(value=B_sample / dt, unit="sequences/s", cores=cores, kind="port",
+                sample=f"oracle port (plain PyTorch CPU fp32, oracle/morec_oracle.py), B={B_sample} of {cfg['B']} users "
+                       f"per step (same L/T/D/encoder), {steps} timed step(s) after thread-count calibration "
+                       f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="morec", choices=["morec", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-users", type=int, default=4)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = dict(CFG)
+    workload = (f"MoRec SASRec+BERT-base end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, T={cfg['T']}, "
+                f"D={cfg['D']}, N={cfg['N']} items, MIND-shape synthetic (BASELINE.json configs[2])")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        W = max(args.warmup, 1)
+        base, dt = time_cpu_oracle(cfg, args.cpu_sample_users, args.steps, W)
+        line = {"impl": "reference", "metric": "training sequences/sec", "value": base["value"], "unit": "sequences/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "sample": base["sample"]},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from transformers import BertConfig, BertModel
+    from idvs.morec_b200 import lib
+    from idvs.morec_b200.model import Model
+    from idvs.morec_b200.optim import FusedAdamW
+    from idvs.morec_b200.synth import synth_batch
+
+    lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    W, K = max(args.warmup, 3), args.steps
+    torch.manual_seed(12345)
+    bert = BertModel(BertConfig(**BERT_BASE))
+    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
+        if i in (197, 198):
+            p.requires_grad = False
+    batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True) for i in range(W + K)]
+    pop = batches[0]["pop_prob"].numpy()
+    model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
+    model.set_compute_dtype(args.mode)
+    model.train()
+    if world > 1:
+        from idvs.morec_b200.parallel import wrap_ddp
+        model_run = wrap_ddp(model, local_rank)
+        core = model
+    else:
+        model_run, core = model, model
+    bert_params = [p for n, p in core.named_parameters() if p.requires_grad and "bert_model" in n]
+    rec_params = [p for n, p in core.named_parameters() if p.requires_grad and "bert_model" not in n]
+    opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
+                      {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+
+    host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
+    resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step(ids, items, lm):
+        opt.zero_grad(set_to_none=True)
+        loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) with live GEMM timing for the roofline
+    for i in range(W):
+        step(*resident[i])
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    # count the GEMM launches of one step, pre-create their events, then time K steps
+    lib.reset_counters()
+    lib.set_gemm_timing(True)
+    step(*resident[W - 1])
+    sync()
+    _, _, per_step = lib.collect_gemm_timing()
+    lib.prepare_gemm_timing(per_step * K + 64)
+    lib.reset_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(K):
+        step(*resident[W + i])
+    e1.record()
+    sync()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    lib.set_gemm_timing(False)
+    gemm_ms, gemm_flops, gemm_n = lib.collect_gemm_timing()
+    launches = lib.launch_count()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms) / K
+    value = cfg["B"] * world / (ms_step / 1e3)
+
+    # ---------------- end to end through the public API: pinned H2D of each batch + D2H of the loss, every step
+    for i in range(2):
+        step(*[t.to(dev, non_blocking=True) for t in host[i]])
+    sync()
+    e0.record()
+    for i in range(K):
+        ids, items, lm = [t.to(dev, non_blocking=True) for t in host[W + i]]
+        loss = step(ids, items, lm)
+        _ = float(loss.detach())             # D2H read of the step's loss (also the reference's NaN check, run.py:249)
+    e1.record()
+    sync()
+    tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    e2e_value = cfg["B"] * world / (float(tms) / K / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "morec::gemm_kernel (tcgen05, all fwd/dgrad/wgrad/scoring launches)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches_timed": gemm_n, "gemm_ms_per_step": gemm_ms / K,
+                "note": {"fp32": "3xTF32 parity mode: 3 tensor-core passes per algorithmic FLOP and kind::tf32 runs at half "
+                                 "the bf16 rate, so the attainable fraction of the bf16 peak is 1/6",
+                         "tf32": "kind::tf32 runs at half the bf16 rate: attainable fraction of the bf16 peak is 1/2",
+                         "bf16": "kind::f16"}[args.mode]}
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        cpu_base, _ = time_cpu_oracle(cfg, args.cpu_sample_users, 1, 1)
+    line = {"metric": "training sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32 (3xTF32 tensor-core emulation)", "tf32": "tf32", "bf16": "bf16"}[args.mode],
+            "data": "synthetic",
+            "config": {"workload": workload, "mode": args.mode, "parallelism": f"dp{world}",
+                       "l2_policy": "every step uses a different batch and streams >10 GB of activations (>> 126 MB L2)",
+                       "dropout": cfg["drop"], "optimizer": "FusedAdamW (2 groups)",
+                       "items_encoded": "non-pad slots only (pad slots are exact zeros in the loss); pad tokens skipped"},
+            "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

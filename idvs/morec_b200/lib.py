@@ -37,10 +37,82 @@ def load():
     return lib
 
 
+_LAUNCHES = 0          # kernels launched through the C ABI since reset_counters()
+_EXTRA = {"morec_inbatch_ce_fwd": 1}   # entry points that launch more than one kernel
+_GEMM_TIMING = False
+_GEMM_EVENTS = []      # (start_event, end_event, flops)
+
+
 def _check(rc, what):
+    global _LAUNCHES
     if rc != 0:
         msg = load().morec_last_error().decode("utf-8", "replace")
         raise MorecError(f"{what} failed (rc={rc}): {msg}")
+    _LAUNCHES += 1 + _EXTRA.get(what, 0)
+
+
+def reset_counters():
+    global _LAUNCHES
+    _LAUNCHES = 0
+    _GEMM_EVENTS.clear()
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def set_gemm_timing(on: bool):
+    """bracket every tcgen05 GEMM launch with CUDA events on the launching stream (bench.py roofline leg)"""
+    global _GEMM_TIMING
+    _GEMM_TIMING = bool(on)
+
+
+def collect_gemm_timing():
+    """-> (total ms, total algorithmic FLOPs, launches); call after torch.cuda.synchronize()"""
+    ms = sum(a.elapsed_time(b) for a, b, _ in _GEMM_EVENTS)
+    fl = sum(f for _, _, f in _GEMM_EVENTS)
+    n = len(_GEMM_EVENTS)
+    _GEMM_EVENTS.clear()
+    return ms, fl, n
+
+
+_EVENT_POOL = []       # pre-created CUDA events (creation costs ~10 us; a record ~1 us)
+_EVENT_NEXT = 0
+
+
+def prepare_gemm_timing(n_launches: int):
+    """pre-create the events for n_launches timed GEMM launches so the timed region only pays cudaEventRecord"""
+    global _EVENT_NEXT
+    while len(_EVENT_POOL) < 2 * n_launches:
+        _EVENT_POOL.append(torch.cuda.Event(enable_timing=True))
+    _EVENT_NEXT = 0
+
+
+def _next_event():
+    global _EVENT_NEXT
+    if _EVENT_NEXT < len(_EVENT_POOL):
+        e = _EVENT_POOL[_EVENT_NEXT]
+    else:
+        e = torch.cuda.Event(enable_timing=True)
+        _EVENT_POOL.append(e)
+    _EVENT_NEXT += 1
+    return e
+
+
+class _timed_gemm:
+    def __init__(self, flops):
+        self.flops = flops
+
+    def __enter__(self):
+        if _GEMM_TIMING:
+            self.e0 = _next_event()
+            self.e1 = _next_event()
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _GEMM_TIMING:
+            self.e1.record()
+            _GEMM_EVENTS.append((self.e0, self.e1, self.flops))
 
 
 def _ptr(t):
@@ -102,9 +174,10 @@ def gemm(A, B, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, ldaux
     dt = gemm_dtype_code(A)
     assert gemm_dtype_code(B) == dt
     out_bf16 = 1 if C.dtype == torch.bfloat16 else 0
-    rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), c_int(M), c_int(N), c_int(K),
-                        c_int(lda), c_int(ldb), c_int(ldc), c_int(ldaux), c_int(int(a_mn)), c_int(int(b_mn)),
-                        c_int(dt), c_int(out_bf16), c_int(epilogue), c_float(alpha), c_int(int(accumulate)), _stream())
+    with _timed_gemm(2.0 * M * N * K):
+        rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), c_int(M), c_int(N), c_int(K),
+                            c_int(lda), c_int(ldb), c_int(ldc), c_int(ldaux), c_int(int(a_mn)), c_int(int(b_mn)),
+                            c_int(dt), c_int(out_bf16), c_int(epilogue), c_float(alpha), c_int(int(accumulate)), _stream())
     _check(rc, "morec_gemm")
 
 

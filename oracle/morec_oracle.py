@@ -270,56 +270,6 @@ def model_forward(p: Dict[str, torch.Tensor], ids: torch.Tensor, items: torch.Te
 
 
 # --------------------------------------------------------------------------------------------------
-# synthetic data of SURVEY.md §8(d) (shared by tests and bench; integer-exact, seeded)
+# synthetic data of SURVEY.md §8(d): lives in the product package (bench.py uses it too); re-exported here
 # --------------------------------------------------------------------------------------------------
-
-def synth_batch(B: int, L: int, N: int, T: int, seed: int, *, modal: bool, mind_shape: bool = True,
-                vocab_lo: int = 1000, vocab_hi: int = 30000, n_users_pop: int = 20000):
-    """MIND-shape synthetic batch: Zipf(1.0) item ids over 1..N, 35 % full-length users and the rest
-    uniform on [3, L] items, left padded; titles of uniform length [6, T] with [CLS]=101 first;
-    popularity p_i computed from a synthetic train split exactly as preprocess.py:71-76 (count / total,
-    p[0] = 1), with every in-batch id guaranteed p > 0.
-    Returns dict(ids [B,L+1] i64, items [C,2T] | [C] i64, log_mask [B,L] f32, pop_prob [N+1] f64,
-    item_content [N+1, 2T] i64 | None).
-    """
-    g = np.random.default_rng(seed)
-    w = 1.0 / np.arange(1, N + 1, dtype=np.float64)
-    w /= w.sum()
-    perm = g.permutation(N) + 1                       # popularity rank -> item id
-
-    def draw(n):
-        return perm[g.choice(N, size=n, p=w)]
-
-    counts = np.zeros(N + 1, dtype=np.float64)
-    pop_draw = draw(n_users_pop * 8)
-    np.add.at(counts, pop_draw, 1.0)
-    ids = np.zeros((B, L + 1), dtype=np.int64)
-    for b in range(B):
-        if (not mind_shape) or g.random() < 0.35:
-            n = L + 1
-        else:
-            n = int(g.integers(3, L + 1))
-        seq = draw(n)
-        ids[b, L + 1 - n:] = seq
-        np.add.at(counts, seq, 1.0)
-    pop = counts[1:] / counts[1:].sum()
-    pop_prob = np.append([1.0], pop)
-    out = dict(ids=torch.from_numpy(ids), log_mask=log_mask_from_ids(torch.from_numpy(ids)),
-               pop_prob=torch.from_numpy(pop_prob))
-    if modal:
-        content = np.zeros((N + 1, 2 * T), dtype=np.int64)
-        lens = g.integers(min(6, T), T + 1, size=N + 1)
-        tok = g.integers(vocab_lo, vocab_hi, size=(N + 1, T))
-        ar = np.arange(T)[None, :]
-        am = (ar < lens[:, None]).astype(np.int64)
-        tok = tok * am
-        tok[:, 0] = 101
-        content[:, :T] = tok
-        content[:, T:] = am
-        content[0] = 0
-        out["item_content"] = torch.from_numpy(content)
-        out["items"] = torch.from_numpy(content[ids.reshape(-1)])
-    else:
-        out["item_content"] = None
-        out["items"] = torch.from_numpy(ids.reshape(-1).copy())
-    return out
+from idvs.morec_b200.synth import synth_batch  # noqa: E402,F401
