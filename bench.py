@@ -26,6 +26,9 @@ import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# batches differ in packed token count, so activation sizes change every step: expandable segments keep the caching
+# allocator from falling back to cudaMalloc/cudaFree (device-synchronising) while it is still growing
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                  intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
@@ -43,50 +46,63 @@ def make_args(cfg):
     return a
 
 
-# ------------------------------------------------------------------------------------------------ clocks sampler
-class ClockSampler:
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockMonitor:
+    """SM clock and throttle reasons of the timed region.
 
-    def start(self):
+    NVML / nvidia-smi queries issued WHILE the step loop runs were measured to stall CUDA launches on these hosts
+    (host-bound step time 35 ms -> 82 ms with a 100 ms polling thread), so the in-region clock is measured on the
+    device itself: after every timed step a one-thread probe kernel (morec_clock_probe, ~20 us) reads clock64 and
+    globaltimer -> SM MHz under load.  NVML is queried immediately before the first timed step is enqueued (GPU hot
+    from the warm-up steps) and immediately after the last one completes: max clock + the union of the throttle /
+    event reasons seen at both edges."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
+    def __init__(self, index, n_probes):
+        import torch
+        self.buf = torch.zeros(n_probes, 2, dtype=torch.int64, device=f"cuda:{index}")
+        self.n = 0
+        self.bits = 0
+        self.smax = None
+        self.h = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index),
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.h = None
+        self.nvml_sm = []
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], 0, set()
-        for (t, line) in self.rows:
-            if t < t0 or t > t1 + 0.3:
-                continue
-            f = [x.strip() for x in line.split(",")]
+    def edge(self):
+        if self.h is None:
+            return
+        try:
             try:
-                sm.append(float(f[0])); smax = max(smax, float(f[1]))
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.nvml_sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+
+    def probe(self):
+        from idvs.morec_b200 import lib
+        if self.n < self.buf.shape[0]:
+            lib.clock_probe(self.buf[self.n])
+            self.n += 1
+
+    def result(self):
+        mhz = sorted(float(c) / float(ns) * 1e3 for c, ns in self.buf[:self.n].cpu().tolist() if ns > 0)
+        if not mhz:
             return None
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": round(mhz[len(mhz) // 2], 1), "sm_mhz_min": round(mhz[0], 1), "sm_max_mhz": self.smax,
+                "reasons": sorted(k for k, m in self.REASONS.items() if self.bits & m), "samples": len(mhz),
+                "nvml_sm_mhz_at_edges": self.nvml_sm,
+                "method": "device clock64/globaltimer probe after every timed step; NVML reasons at both edges"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
@@ -161,6 +177,49 @@ def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
                        f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt
 
 
+def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0):
+    """model + optimizer + synthetic batches exactly as the reference loop builds them (run.py:127-162);
+    returns (step_fn, pinned host batches, device-resident batches, H2D bytes per step)"""
+    import torch
+    from transformers import BertConfig, BertModel
+    from idvs.morec_b200.model import Model
+    from idvs.morec_b200.optim import FusedAdamW
+    from idvs.morec_b200.synth import synth_batch
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(12345)
+    bert = BertModel(BertConfig(**BERT_BASE))
+    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
+        if i in (197, 198):
+            p.requires_grad = False
+    batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True)
+               for i in range(n_batches)]
+    pop = batches[0]["pop_prob"].numpy()
+    model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
+    model.set_compute_dtype(mode)
+    model.train()
+    if world > 1:
+        from idvs.morec_b200.parallel import wrap_ddp
+        model_run = wrap_ddp(model, local_rank)
+    else:
+        model_run = model
+    bert_params = [p for n, p in model.named_parameters() if p.requires_grad and "bert_model" in n]
+    rec_params = [p for n, p in model.named_parameters() if p.requires_grad and "bert_model" not in n]
+    opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
+                      {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+    host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
+    resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step(ids, items, lm):
+        opt.zero_grad(set_to_none=True)
+        loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step, host, resident, h2d_bytes
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -195,11 +254,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from transformers import BertConfig, BertModel
     from idvs.morec_b200 import lib
-    from idvs.morec_b200.model import Model
-    from idvs.morec_b200.optim import FusedAdamW
-    from idvs.morec_b200.synth import synth_batch
 
     lib.load()
     torch.cuda.set_device(local_rank)
@@ -207,78 +262,59 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
-    torch.manual_seed(12345)
-    bert = BertModel(BertConfig(**BERT_BASE))
-    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
-        if i in (197, 198):
-            p.requires_grad = False
-    batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True) for i in range(W + K)]
-    pop = batches[0]["pop_prob"].numpy()
-    model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
-    model.set_compute_dtype(args.mode)
-    model.train()
-    if world > 1:
-        from idvs.morec_b200.parallel import wrap_ddp
-        model_run = wrap_ddp(model, local_rank)
-        core = model
-    else:
-        model_run, core = model, model
-    bert_params = [p for n, p in core.named_parameters() if p.requires_grad and "bert_model" in n]
-    rec_params = [p for n, p in core.named_parameters() if p.requires_grad and "bert_model" not in n]
-    opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
-                      {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
-
-    host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
-    resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
-
-    def step(ids, items, lm):
-        opt.zero_grad(set_to_none=True)
-        loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank)
-        loss.backward()
-        opt.step()
-        return loss
+    step, host, resident, h2d_bytes = setup_training(cfg, args.mode, W + K, rank, world, local_rank)
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`) with live GEMM timing for the roofline
-    for i in range(W):
+    # ---------------- device-resident throughput (`value`): K steps, batches already in HBM
+    # warm-up: W steps, the first one on the batch with the most real tokens so the allocator reaches its
+    # steady-state footprint before anything is timed
+    big = max(range(len(host)), key=lambda i: int((host[i][1][:, :, cfg["T"]:] != 0).sum()))
+    step(*resident[big])
+    for i in range(W - 1):
         step(*resident[i])
     sync()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    # count the GEMM launches of one step, pre-create their events, then time K steps
-    lib.reset_counters()
-    lib.set_gemm_timing(True)
-    step(*resident[W - 1])
-    sync()
-    _, _, per_step = lib.collect_gemm_timing()
-    lib.prepare_gemm_timing(per_step * K + 64)
+    mon = ClockMonitor(local_rank, K) if rank == 0 else None
     lib.reset_counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    if mon:
+        mon.edge()
     t_wall0 = time.time()
     e0.record()
     for i in range(K):
         step(*resident[W + i])
+        if mon:
+            mon.probe()
     e1.record()
+    t_issue = time.time() - t_wall0          # host time to enqueue K steps (includes the in-step size syncs)
     sync()
-    t_wall1 = time.time()
+    if mon:
+        mon.edge()
     ms = e0.elapsed_time(e1)
-    lib.set_gemm_timing(False)
-    gemm_ms, gemm_flops, gemm_n = lib.collect_gemm_timing()
     launches = lib.launch_count()
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = mon.result() if mon else None
     tms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_step = float(tms) / K
     value = cfg["B"] * world / (ms_step / 1e3)
+
+    # ---------------- roofline leg: the same K steps again with every tcgen05 GEMM launch bracketed by CUDA events
+    # on the launching stream (kept out of the `value` loop: ~350 event records per step perturb the host side)
+    lib.set_gemm_timing(True)
+    step(*resident[W - 1])
+    sync()
+    _, _, per_step = lib.collect_gemm_timing()
+    lib.prepare_gemm_timing(per_step * K + 64)
+    for i in range(K):
+        step(*resident[W + i])
+    sync()
+    lib.set_gemm_timing(False)
+    gemm_ms, gemm_flops, gemm_n = lib.collect_gemm_timing()
 
     # ---------------- end to end through the public API: pinned H2D of each batch + D2H of the loss, every step
     for i in range(2):
@@ -328,7 +364,7 @@ def main():
                        "dropout": cfg["drop"], "optimizer": "FusedAdamW (2 groups)",
                        "items_encoded": "non-pad slots only (pad slots are exact zeros in the loss); pad tokens skipped"},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+            "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

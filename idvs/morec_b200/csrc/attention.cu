@@ -45,13 +45,77 @@ __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-// cooperative (one warp) load of rows [row0, row0+len) x cols [col0, col0+w) into tile[32][AT_DCH] (fp32)
+// cooperative (one warp) load of rows [row0, row0+len) x cols [col0, col0+w) into tile[32][AT_DCH] (fp32), 4 elements
+// per lane per iteration (w % 4 == 0, rows 16-byte aligned)
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
 template <typename T>
 __device__ __forceinline__ void load_tile(float* tile, const T* base, int ld, int row0, int len, int col0, int w,
                                           int lane) {
-    for (int idx = lane; idx < len * w; idx += 32) {
-        const int r = idx / w, c = idx - r * w;
-        tile[r * AT_DCH + c] = ldf<T>(base + (size_t)(row0 + r) * ld + col0 + c);
+    const int nv = w >> 2;
+    for (int idx = lane; idx < len * nv; idx += 32) {
+        const int r = idx / nv, c = (idx - r * nv) << 2;
+        *reinterpret_cast<float4*>(tile + r * AT_DCH + c) = ld4<T>(base + (size_t)(row0 + r) * ld + col0 + c);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+// per-lane store of a 64-wide (or narrower) register slice to a row
+template <typename T>
+__device__ __forceinline__ void store_row(T* row, const float (&v)[AT_DCH], int w) {
+#pragma unroll
+    for (int t = 0; t < AT_DCH / 4; ++t)
+        if (4 * t < w) st4<T>(row + 4 * t, make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]));
+}
+
+// per-lane load of one 64-wide (or narrower) slice of a row into registers
+template <typename T>
+__device__ __forceinline__ void load_row(float (&v)[AT_DCH], const T* row, int w, bool active) {
+#pragma unroll
+    for (int t = 0; t < AT_DCH / 4; ++t) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && 4 * t < w) x = ld4<T>(row + 4 * t);
+        v[4 * t] = x.x; v[4 * t + 1] = x.y; v[4 * t + 2] = x.z; v[4 * t + 3] = x.w;
+    }
+}
+
+// acc[jj] += <v, tile[j0 + jj][0..w)> for 4 keys at once (4 independent FMA chains)
+__device__ __forceinline__ void dot4keys(const float (&v)[AT_DCH], const float* tile, int j0, int w, float& a0, float& a1,
+                                         float& a2, float& a3) {
+    const float4* k0 = reinterpret_cast<const float4*>(tile + (j0 + 0) * AT_DCH);
+    const float4* k1 = reinterpret_cast<const float4*>(tile + (j0 + 1) * AT_DCH);
+    const float4* k2 = reinterpret_cast<const float4*>(tile + (j0 + 2) * AT_DCH);
+    const float4* k3 = reinterpret_cast<const float4*>(tile + (j0 + 3) * AT_DCH);
+    const int nt = w >> 2;
+#pragma unroll
+    for (int t = 0; t < AT_DCH / 4; ++t) {
+        if (t < nt) {
+            const float4 x0 = k0[t], x1 = k1[t], x2 = k2[t], x3 = k3[t];
+            a0 += v[4 * t] * x0.x + v[4 * t + 1] * x0.y + v[4 * t + 2] * x0.z + v[4 * t + 3] * x0.w;
+            a1 += v[4 * t] * x1.x + v[4 * t + 1] * x1.y + v[4 * t + 2] * x1.z + v[4 * t + 3] * x1.w;
+            a2 += v[4 * t] * x2.x + v[4 * t + 1] * x2.y + v[4 * t + 2] * x2.z + v[4 * t + 3] * x2.w;
+            a3 += v[4 * t] * x3.x + v[4 * t + 1] * x3.y + v[4 * t + 2] * x3.z + v[4 * t + 3] * x3.w;
+        }
     }
 }
 
@@ -83,29 +147,11 @@ __device__ __forceinline__ void scores_softmax(const AttnParams& p, float* tile,
         load_tile<T>(tile, K, p.ld, row0, len, h * p.head_dim + dc, w, lane);
         __syncwarp();
         float qv[AT_DCH];
-        if (lane < len) {
-            const T* qr = Q + (size_t)(row0 + lane) * p.ld + h * p.head_dim + dc;
+        load_row<T>(qv, Q + (size_t)(row0 + (lane < len ? lane : 0)) * p.ld + h * p.head_dim + dc, w, lane < len);
+        // rows >= len of the tile hold stale data: their scores are discarded below (pr[j >= len] := 0)
 #pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) qv[t] = t < w ? ldf<T>(qr + t) : 0.f;
-        } else {
-#pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) qv[t] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < AT_MAXL; ++j) {
-            if (j < len) {
-                float acc = 0.f;
-                const float4* kr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
-                const int nt = w >> 2;
-#pragma unroll
-                for (int t = 0; t < AT_DCH / 4; ++t) {
-                    if (t < nt) {
-                        const float4 kk = kr[t];
-                        acc += qv[4 * t] * kk.x + qv[4 * t + 1] * kk.y + qv[4 * t + 2] * kk.z + qv[4 * t + 3] * kk.w;
-                    }
-                }
-                pr[j] += acc;
-            }
+        for (int j0 = 0; j0 < AT_MAXL; j0 += 4) {
+            if (j0 < len) dot4keys(qv, tile, j0, w, pr[j0], pr[j0 + 1], pr[j0 + 2], pr[j0 + 3]);
         }
     }
     float m = -INFINITY;
@@ -187,9 +233,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(const AttnParam
             }
             if (lane < len) {
                 T* orow = O + (size_t)(row0 + lane) * p.ld_o + h * p.head_dim + dc;
-#pragma unroll
-                for (int t = 0; t < AT_DCH; ++t)
-                    if (t < w) stf<T>(orow + t, ov[t]);
+store_row<T>(orow, ov, w);
             }
         }
     }
@@ -228,29 +272,10 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
             load_tile<T>(tile, V, p.ld, row0, len, col_h + dc, w, lane);
             __syncwarp();
             float gv[AT_DCH];
-            if (lane < len) {
-                const T* gr = dO + (size_t)(row0 + lane) * p.ld_o + col_h + dc;
+            load_row<T>(gv, dO + (size_t)(row0 + (lane < len ? lane : 0)) * p.ld_o + col_h + dc, w, lane < len);
 #pragma unroll
-                for (int t = 0; t < AT_DCH; ++t) gv[t] = t < w ? ldf<T>(gr + t) : 0.f;
-            } else {
-#pragma unroll
-                for (int t = 0; t < AT_DCH; ++t) gv[t] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < AT_MAXL; ++j) {
-                if (j < len) {
-                    float acc = 0.f;
-                    const float4* vr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
-                    const int nt = w >> 2;
-#pragma unroll
-                    for (int t = 0; t < AT_DCH / 4; ++t) {
-                        if (t < nt) {
-                            const float4 vv = vr[t];
-                            acc += gv[4 * t] * vv.x + gv[4 * t + 1] * vv.y + gv[4 * t + 2] * vv.z + gv[4 * t + 3] * vv.w;
-                        }
-                    }
-                    dp[j] += acc;
-                }
+            for (int j0 = 0; j0 < AT_MAXL; j0 += 4) {
+                if (j0 < len) dot4keys(gv, tile, j0, w, dp[j0], dp[j0 + 1], dp[j0 + 2], dp[j0 + 3]);
             }
         }
         // ---- softmax backward (with dropout on P): dS = P * (dP - sum_k P_k dP_k), dP = keep * dP~ / (1-p)
@@ -261,7 +286,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
 #pragma unroll
             for (int j = 0; j < AT_MAXL; ++j) {
                 const float keep = ((kb >> j) & 1u) ? sc : 0.f;
-                dp[j] *= keep;                 // dP (w.r.t. un-dropped probabilities)
+                dp[j] = j < len ? dp[j] * keep : 0.f;   // dP w.r.t. un-dropped probabilities (stale keys -> 0)
                 dsum += pr[j] * dp[j];
                 Pw[lane * 33 + j] = pr[j] * keep;   // P~ for dV
             }
@@ -293,9 +318,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
             }
             if (lane < len) {
                 T* r = dQ + (size_t)(row0 + lane) * p.ld + col_h + dc;
-#pragma unroll
-                for (int t = 0; t < AT_DCH; ++t)
-                    if (t < w) stf<T>(r + t, acc[t]);
+store_row<T>(r, acc, w);
             }
         }
         // ---- dK_j = sum_i dS_ij Q_i        (lane = key j; Q chunk broadcast from smem)
@@ -318,9 +341,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
             }
             if (lane < len) {
                 T* r = dK + (size_t)(row0 + lane) * p.ld + col_h + dc;
-#pragma unroll
-                for (int t = 0; t < AT_DCH; ++t)
-                    if (t < w) stf<T>(r + t, acc[t]);
+store_row<T>(r, acc, w);
             }
         }
         // ---- dV_j = sum_i P~_ij dO_i       (lane = key j; dO chunk broadcast from smem)
@@ -343,9 +364,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
             }
             if (lane < len) {
                 T* r = dV + (size_t)(row0 + lane) * p.ld + col_h + dc;
-#pragma unroll
-                for (int t = 0; t < AT_DCH; ++t)
-                    if (t < w) stf<T>(r + t, acc[t]);
+store_row<T>(r, acc, w);
             }
         }
         __syncwarp();

@@ -93,6 +93,67 @@ struct StdEpi {
         }
     }
 
+    __device__ __forceinline__ static void chunk(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                                                 EpiStore& st, const uint32_t (&v)[32], int c, int row, int row0,
+                                                 int n0, bool add_bias, const TileSched& s) {
+        const int col0 = n0 + c * 32;
+        const bool obf = s.out_bf16 != 0;
+        const int ns = ep.mode == MOREC_EPI_GELU ? 2 : 1;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha;
+        if (add_bias) {
+            if (col0 + 32 <= s.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+                    x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < s.N) x[j] += __ldg(ep.bias + col0 + j);
+            }
+        }
+        switch (ep.mode) {
+            case MOREC_EPI_GELU: {
+                // pre-activation to C2 first (kept for the backward), then the activation to C
+                st.put(&tmC2, x, c, obf, 1, 2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                break;
+            }
+            case MOREC_EPI_GELU_NOSAVE: {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                break;
+            }
+            case MOREC_EPI_RELU: {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                break;
+            }
+            case MOREC_EPI_MUL_GELU_GRAD: {
+                float a[32];
+                load_aux(ep, a, row, col0, s.M, s.N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(a[j]);
+                break;
+            }
+            case MOREC_EPI_MUL_RELU_GRAD: {
+                float a[32];
+                load_aux(ep, a, row, col0, s.M, s.N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
+                break;
+            }
+            default:
+                break;
+        }
+        st.put(&tmC, x, c, obf, 0, ns);
+        st.end_chunk(c, n0, row0, obf, s.accumulate != 0, ns);
+    }
+
     template <int BLOCK_N>
     __device__ __forceinline__ static void tile(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                                                 uint32_t taddr, EpiStore& st, int m0, int q, int n0, int split,
@@ -103,67 +164,21 @@ struct StdEpi {
         int c_end = (s.N - n0 + 31) / 32;
         if (c_end > BLOCK_N / 32) c_end = BLOCK_N / 32;
         if (s.out_bf16) c_end = (c_end + 1) & ~1;
+        st.c_end = c_end;
         const bool add_bias = ep.bias != nullptr && split == 0;
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
 #pragma unroll 1
-        for (int c = 0; c < c_end; ++c) {
-            const int col0 = n0 + c * 32;
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
+        for (int c = 0; c < c_end; c += 2) {
             tc_wait_ld();
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha;
-            if (add_bias) {
-                if (col0 + 32 <= s.N) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
-                        x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < s.N) x[j] += __ldg(ep.bias + col0 + j);
-                }
+            if (c + 1 < c_end) tmem_ld32(taddr + (c + 1) * 32, vb);
+            chunk(ep, tmC, tmC2, st, va, c, row, row0, n0, add_bias, s);
+            if (c + 1 < c_end) {
+                tc_wait_ld();
+                if (c + 2 < c_end) tmem_ld32(taddr + (c + 2) * 32, va);
+                chunk(ep, tmC, tmC2, st, vb, c + 1, row, row0, n0, add_bias, s);
             }
-            switch (ep.mode) {
-                case MOREC_EPI_LINEAR:
-                    break;
-                case MOREC_EPI_GELU: {
-                    // pre-activation to C2 first (kept for the backward), then the activation to C
-                    st.emit(&tmC2, x, c, n0, row0, s.out_bf16 != 0, false, 1, 2);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-                    break;
-                }
-                case MOREC_EPI_GELU_NOSAVE: {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-                    break;
-                }
-                case MOREC_EPI_RELU: {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                    break;
-                }
-                case MOREC_EPI_MUL_GELU_GRAD: {
-                    float a[32];
-                    load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(a[j]);
-                    break;
-                }
-                case MOREC_EPI_MUL_RELU_GRAD: {
-                    float a[32];
-                    load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
-                    break;
-                }
-                default:
-                    break;
-            }
-            st.emit(&tmC, x, c, n0, row0, s.out_bf16 != 0, s.accumulate != 0, 0, ep.mode == MOREC_EPI_GELU ? 2 : 1);
         }
     }
 };

@@ -93,77 +93,82 @@ struct Cfg {
     static_assert(STAGES >= 2, "not enough smem stages");
 };
 
-// Staging + TMA store of one 32-row sub-tile held as 32 fp32 per thread (thread == row).
-// fp32 output : 32 columns  -> one 128B row, stored immediately.
-// bf16 output : 32 columns  -> half a 128B row; the store is issued after the odd chunk.
+// Staging + TMA store of the epilogue output.  Each epilogue warp owns `nsub` sub-buffers of 32 rows x 128 bytes
+// (SWIZZLE_128B; 32 fp32 or 64 bf16 columns each).  Chunks of 32 accumulator columns (thread == row, 32 registers) are
+// written into the sub-buffers of the current GROUP; when the group is full (or the tile ends) ONE fence + ONE
+// elected thread issues all its TMA stores (or TMA reduce-adds) and commits them as one bulk group.  With the default
+// 4 sub-buffers a group is 128 fp32 / 256 bf16 columns of one output stream (half of that with two streams, e.g.
+// GELU writing pre-activation + activation), so the per-chunk fence / sync / wait overhead of a naive epilogue is
+// paid once or twice per tile instead of eight times.
 struct EpiStore {
-    uint8_t* bufs;     // this warp's staging buffers
-    int buf;           // rotating index
+    uint8_t* bufs;            // this warp's staging sub-buffers
     int lane;
-    int nbufs;         // 4 (default) or 2 (3xTF32 configuration)
-    // before filling `nslots` buffers, at most nbufs - nslots earlier stores may still be reading theirs
-    __device__ __forceinline__ void begin(int nslots) {
-        if (lane == 0) {
-            const int allow = nbufs - nslots;
-            if (allow >= 2) tma_store_wait_read<2>();
-            else if (allow == 1) tma_store_wait_read<1>();
-            else tma_store_wait_read<0>();
+    int nsub;                 // 4 (default) or 2 (3xTF32 configuration)
+    int c_end;                // number of 32-column chunks of the current tile (set by the epilogue)
+    const CUtensorMap* tm[2]; // output tensor map per stream (0: C, 1: C2)
+
+    __device__ __forceinline__ void put(const CUtensorMap* tmap, const float (&x)[32], int c, bool out_bf16, int stream,
+                                        int nstreams) {
+        const int cps = out_bf16 ? 2 : 1;                 // chunks per sub-buffer
+        const int S = nsub / nstreams;                    // sub-buffers per stream per group
+        const int G = S * cps;                            // chunks per group
+        const int g = c % G;
+        if (g == 0 && stream == nstreams - 1) {           // first write of a new group: previous stores must have
+            if (lane == 0) tma_store_wait_read<0>();      // finished reading the staging memory
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    __device__ __forceinline__ void put_f32(const float (&x)[32], int slot) {
-        uint8_t* rowp = bufs + ((buf + slot) % nbufs) * kEpiBufBytes + lane * 128;
+        tm[stream] = tmap;
+        uint8_t* rowp = bufs + (stream * S + g / cps) * kEpiBufBytes + lane * 128;
+        if (!out_bf16) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int pj = j ^ (lane & 7);
-            *reinterpret_cast<float4*>(rowp + pj * 16) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        }
-    }
-    __device__ __forceinline__ void put_bf16(const float (&x)[32], int half, int slot) {
-        uint8_t* rowp = bufs + ((buf + slot) % nbufs) * kEpiBufBytes + lane * 128;
+            for (int j = 0; j < 8; ++j) {
+                const int pj = j ^ (lane & 7);
+                *reinterpret_cast<float4*>(rowp + pj * 16) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
+        } else {
+            const int half = g % cps;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int pj = (half * 4 + j) ^ (lane & 7);
-            __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]);
-            __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
-            __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]);
-            __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-            u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
-            *reinterpret_cast<uint4*>(rowp + pj * 16) = u;
+            for (int j = 0; j < 4; ++j) {
+                const int pj = (half * 4 + j) ^ (lane & 7);
+                __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]);
+                __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
+                __nv_bfloat162 cc = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]);
+                __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+                u.z = *reinterpret_cast<uint32_t*>(&cc); u.w = *reinterpret_cast<uint32_t*>(&d);
+                *reinterpret_cast<uint4*>(rowp + pj * 16) = u;
+            }
         }
     }
-    __device__ __forceinline__ void commit(const CUtensorMap* tm, int col0, int row0, bool reduce_add, int slot = 0) {
+    // call once per chunk after all streams were put: flushes the group when it is full or the tile ends
+    __device__ __forceinline__ void end_chunk(int c, int n0, int row0, bool out_bf16, bool reduce_add, int nstreams) {
+        const int cps = out_bf16 ? 2 : 1;
+        const int S = nsub / nstreams;
+        const int G = S * cps;
+        const int g = c % G;
+        if (g != G - 1 && c != c_end - 1) return;
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            const uint32_t src = smem_u32(bufs + ((buf + slot) % nbufs) * kEpiBufBytes);
-            if (reduce_add) tma_reduce_add_2d(tm, src, col0, row0);
-            else tma_store_2d(tm, src, col0, row0);
+            const int nfilled = g / cps + 1;              // sub-buffers filled per stream
+            const int col_base = n0 + (c - g) * 32;
+            const int cols_per_sub = out_bf16 ? 64 : 32;
+            for (int st = 0; st < nstreams; ++st) {
+                for (int sb = 0; sb < nfilled; ++sb) {
+                    const uint32_t src = smem_u32(bufs + (st * S + sb) * kEpiBufBytes);
+                    if (reduce_add) tma_reduce_add_2d(tm[st], src, col_base + sb * cols_per_sub, row0);
+                    else tma_store_2d(tm[st], src, col_base + sb * cols_per_sub, row0);
+                }
+            }
             tma_store_commit();
         }
     }
-    __device__ __forceinline__ void advance(int n) { buf = (buf + n) % nbufs; }
-    // One 32-column chunk `c` of the tile whose first column is n0.  `slot`/`nslots`: an epilogue with two output
-    // streams emits slot 1 (C2) then slot 0 (C) for every chunk; the buffer ring advances once per chunk (fp32) or
-    // once per chunk pair (bf16) after the LAST slot has been emitted.
-    __device__ __forceinline__ void emit(const CUtensorMap* tm, const float (&x)[32], int c, int n0, int row0,
+    // compatibility helper used by single-stream epilogues
+    __device__ __forceinline__ void emit(const CUtensorMap* tmap, const float (&x)[32], int c, int n0, int row0,
                                          bool out_bf16, bool reduce_add, int slot = 0, int nslots = 1) {
-        const bool first = slot == nslots - 1, last = slot == 0;
-        if (!out_bf16) {
-            if (first) begin(nslots);
-            put_f32(x, slot);
-            commit(tm, n0 + c * 32, row0, reduce_add, slot);
-            if (last) advance(nslots);
-        } else {
-            if ((c & 1) == 0 && first) begin(nslots);
-            put_bf16(x, c & 1, slot);
-            if (c & 1) {
-                commit(tm, n0 + (c - 1) * 32, row0, false, slot);
-                if (last) advance(nslots);
-            }
-        }
+        put(tmap, x, c, out_bf16, slot, nslots);
+        if (slot == 0) end_chunk(c, n0, row0, out_bf16, reduce_add, nslots);
     }
 };
 
@@ -349,8 +354,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int q = warp - 4;  // TMEM lane quarter == warp % 4
         EpiStore st;
         st.bufs = epi_base + q * (C::EPI_BUFS * kEpiBufBytes);
-        st.nbufs = C::EPI_BUFS;
-        st.buf = 0;
+        st.nsub = C::EPI_BUFS;
+        st.c_end = 0;
         st.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;

@@ -129,6 +129,7 @@ struct CeBwdEpi {
         int c_end = (s.N - n0 + 31) / 32;
         if (c_end > BLOCK_N / 32) c_end = BLOCK_N / 32;
         if (s.out_bf16) c_end = (c_end + 1) & ~1;
+        st.c_end = c_end;
 #pragma unroll 1
         for (int c = 0; c < c_end; ++c) {
             const int col0 = n0 + c * 32;

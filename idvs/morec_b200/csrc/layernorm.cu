@@ -134,8 +134,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
     const float sc_pre = p.p_pre > 0.f ? 1.f / (1.f - p.p_pre) : 1.f;
     const float sc_post = p.p_post > 0.f ? 1.f / (1.f - p.p_post) : 1.f;
     float4 ag[NV], ab[NV], ax[NV];   // dgamma, dbeta, dbias partials
+    float4 gam[NV], bet[NV], igam[NV];   // this lane's columns of gamma, beta, 1/gamma (loop invariant)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) ag[j] = ab[j] = ax[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < NV; ++j) {
+        ag[j] = ab[j] = ax[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = lane + 32 * j;
+        if (i < nv) {
+            gam[j] = *reinterpret_cast<const float4*>(p.gamma + 4 * i);
+            bet[j] = *reinterpret_cast<const float4*>(p.beta + 4 * i);
+            igam[j] = make_float4(1.f / gam[j].x, 1.f / gam[j].y, 1.f / gam[j].z, 1.f / gam[j].w);
+        } else {
+            gam[j] = bet[j] = igam[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 
     for (int row = blockIdx.x * LN_WARPS + warp; row < p.M; row += gridDim.x * LN_WARPS) {
         const T* dyr = reinterpret_cast<const T*>(p.dy) + (size_t)row * p.H;
@@ -152,10 +163,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
                 if (dy2r) { const float4 e = load4<T>(dy2r + 4 * i); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
                 if (p.p_post > 0.f) d = drop4(d, p.seed, p.off_post + (uint64_t)row * nv + i, th_post, sc_post);
                 const float4 yv = load4<T>(yr + 4 * i);
-                const float4 ga = *reinterpret_cast<const float4*>(p.gamma + 4 * i);
-                const float4 be = *reinterpret_cast<const float4*>(p.beta + 4 * i);
+                const float4 ga = gam[j], be = bet[j], ig = igam[j];
                 float4 h;
-                h.x = (yv.x - be.x) / ga.x; h.y = (yv.y - be.y) / ga.y; h.z = (yv.z - be.z) / ga.z; h.w = (yv.w - be.w) / ga.w;
+                h.x = (yv.x - be.x) * ig.x; h.y = (yv.y - be.y) * ig.y; h.z = (yv.z - be.z) * ig.z; h.w = (yv.w - be.w) * ig.w;
                 ag[j].x += d.x * h.x; ag[j].y += d.y * h.y; ag[j].z += d.z * h.z; ag[j].w += d.w * h.w;
                 ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
                 d.x *= ga.x; d.y *= ga.y; d.z *= ga.z; d.w *= ga.w;

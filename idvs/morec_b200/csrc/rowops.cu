@@ -151,22 +151,40 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------- AdamW (multi-tensor)
-struct AdamChunk {
+// One entry per parameter tensor; CTAs walk fixed-size chunks and find their tensor by binary search in the
+// exclusive prefix sum of per-tensor chunk counts (chunk_start[n_tensors + 1]).
+struct AdamTensor {
     float* p; const float* g; float* m; float* v; __nv_bfloat16* p_bf16;
     int n; float lr, wd;
 };
+constexpr int ADAM_CHUNK = 16384;
 
-__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamChunk* __restrict__ chunks, int n_chunks,
-                                                          float beta1, float beta2, float eps, float bc1, float bc2,
-                                                          const float* __restrict__ inv_scale,
+__device__ __forceinline__ int find_tensor(const int* __restrict__ chunk_start, int n_tensors, int chunk) {
+    int lo = 0, hi = n_tensors;   // chunk_start[lo] <= chunk < chunk_start[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_start[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ tensors,
+                                                          const int* __restrict__ chunk_start, int n_tensors,
+                                                          int n_chunks, float beta1, float beta2, float eps, float bc1,
+                                                          float bc2, const float* __restrict__ inv_scale,
                                                           const float* __restrict__ found_inf) {
     // found_inf != 0 -> skip the whole step (GradScaler semantics)
     if (found_inf && *found_inf != 0.f) return;
     const float gs = inv_scale ? *inv_scale : 1.f;
+    const float rs2 = rsqrtf(bc2);
     for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
-        const AdamChunk ch = chunks[ci];
-        for (int i = threadIdx.x * 4; i < ch.n; i += blockDim.x * 4) {
-            if (i + 4 <= ch.n) {
+        const int t = find_tensor(chunk_start, n_tensors, ci);
+        const AdamTensor ch = tensors[t];
+        const int e0 = (ci - chunk_start[t]) * ADAM_CHUNK;
+        const int e1 = min(ch.n, e0 + ADAM_CHUNK);
+        const float decay = 1.f - ch.lr * ch.wd, step = ch.lr / bc1;
+        for (int i = e0 + threadIdx.x * 4; i < e1; i += blockDim.x * 4) {
+            if (i + 4 <= e1) {
                 float4 p = *reinterpret_cast<float4*>(ch.p + i);
                 float4 g = *reinterpret_cast<const float4*>(ch.g + i);
                 float4 m = *reinterpret_cast<float4*>(ch.m + i);
@@ -175,23 +193,22 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamChunk* __res
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float gg = gp[k] * gs;
-                    pp[k] *= (1.f - ch.lr * ch.wd);
+                    pp[k] *= decay;
                     mp[k] = beta1 * mp[k] + (1.f - beta1) * gg;
                     vp[k] = beta2 * vp[k] + (1.f - beta2) * gg * gg;
-                    const float denom = sqrtf(vp[k]) / sqrtf(bc2) + eps;
-                    pp[k] -= (ch.lr / bc1) * (mp[k] / denom);
+                    pp[k] -= step * (mp[k] / (sqrtf(vp[k]) * rs2 + eps));
                 }
                 *reinterpret_cast<float4*>(ch.p + i) = p;
                 *reinterpret_cast<float4*>(ch.m + i) = m;
                 *reinterpret_cast<float4*>(ch.v + i) = v;
                 if (ch.p_bf16) st4<__nv_bfloat16>(ch.p_bf16 + i, p);
             } else {
-                for (int k = i; k < ch.n; ++k) {
+                for (int k = i; k < e1; ++k) {
                     const float gg = ch.g[k] * gs;
-                    float pk = ch.p[k] * (1.f - ch.lr * ch.wd);
+                    float pk = ch.p[k] * decay;
                     const float mk = beta1 * ch.m[k] + (1.f - beta1) * gg;
                     const float vk = beta2 * ch.v[k] + (1.f - beta2) * gg * gg;
-                    pk -= (ch.lr / bc1) * (mk / (sqrtf(vk) / sqrtf(bc2) + eps));
+                    pk -= step * (mk / (sqrtf(vk) * rs2 + eps));
                     ch.p[k] = pk; ch.m[k] = mk; ch.v[k] = vk;
                     if (ch.p_bf16) ch.p_bf16[k] = __float2bfloat16(pk);
                 }
@@ -200,18 +217,33 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamChunk* __res
     }
 }
 
-// max |g| finite check over chunks: found_inf = 1 if any grad is inf/nan
-__global__ void __launch_bounds__(256) grad_check_kernel(const AdamChunk* __restrict__ chunks, int n_chunks,
-                                                         float* __restrict__ found_inf) {
+// found_inf = 1 if any gradient is inf/nan
+__global__ void __launch_bounds__(256) grad_check_kernel(const AdamTensor* __restrict__ tensors,
+                                                         const int* __restrict__ chunk_start, int n_tensors,
+                                                         int n_chunks, float* __restrict__ found_inf) {
     bool bad = false;
     for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
-        const AdamChunk ch = chunks[ci];
-        for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
-            const float g = ch.g[i];
-            bad |= !(fabsf(g) <= 3.0e38f);
-        }
+        const int t = find_tensor(chunk_start, n_tensors, ci);
+        const AdamTensor ch = tensors[t];
+        const int e0 = (ci - chunk_start[t]) * ADAM_CHUNK;
+        const int e1 = min(ch.n, e0 + ADAM_CHUNK);
+        for (int i = e0 + threadIdx.x; i < e1; i += blockDim.x) bad |= !(fabsf(ch.g[i]) <= 3.0e38f);
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.f;
+}
+
+// SM clock probe: spins ~20 us and reports (elapsed SM cycles, elapsed ns) so the host can derive the SM clock
+// under load without touching NVML inside a timed region.
+__global__ void clock_probe_kernel(unsigned long long* out) {
+    unsigned long long t0, t1, c0, c1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    c0 = clock64();
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < 20000ull);
+    c1 = clock64();
+    out[0] = c1 - c0;
+    out[1] = t1 - t0;
 }
 
 static int grid_for(size_t work, int threads) {
@@ -312,20 +344,31 @@ extern "C" int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vo
     return MOREC_OK;
 }
 
-// chunks: device array of MorecAdamChunk (see header), built once by the host optimizer wrapper
-extern "C" int morec_adamw_multi(const void* chunks, int n_chunks, float beta1, float beta2, float eps, int step,
-                                 const float* inv_scale, float* found_inf, int check_finite, void* stream) {
-    MOREC_CHECK_ARG(chunks, "adamw_multi: null chunk table");
-    static_assert(sizeof(AdamChunk) == sizeof(MorecAdamChunk), "ABI struct mismatch");
-    if (n_chunks <= 0) return MOREC_OK;
+// table: device buffer = n_tensors MorecAdamTensor records followed by (n_tensors + 1) int32 chunk offsets
+extern "C" int morec_adamw_chunk_elems(void) { return ADAM_CHUNK; }
+
+extern "C" int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
+                                 float beta1, float beta2, float eps, int step, const float* inv_scale,
+                                 float* found_inf, int check_finite, void* stream) {
+    MOREC_CHECK_ARG(tensors && chunk_start, "adamw_multi: null table");
+    static_assert(sizeof(AdamTensor) == sizeof(MorecAdamTensor), "ABI struct mismatch");
+    if (n_chunks <= 0 || n_tensors <= 0) return MOREC_OK;
     const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     const int grid = n_chunks < num_sms() * 8 ? n_chunks : num_sms() * 8;
     if (check_finite && found_inf) {
-        grad_check_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, n_chunks, found_inf);
+        grad_check_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors,
+                                                                 n_chunks, found_inf);
         MOREC_LAUNCH_CHECK();
     }
-    adamw_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamChunk*)chunks, n_chunks, beta1, beta2, eps, bc1,
-                                                              bc2, inv_scale, found_inf);
+    adamw_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors, n_chunks,
+                                                              beta1, beta2, eps, bc1, bc2, inv_scale, found_inf);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_clock_probe(uint64_t* out_cycles_ns, void* stream) {
+    MOREC_CHECK_ARG(out_cycles_ns, "clock_probe: null output");
+    clock_probe_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)out_cycles_ns);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

@@ -33,6 +33,31 @@ def load():
     lib.morec_last_error.restype = c_char_p
     lib.morec_abi_version.restype = c_int
     lib.morec_device_sms.restype = c_int
+    P, I, F, U, L = c_void_p, c_int, c_float, c_uint64, c_int64
+    sig = {
+        "morec_gemm": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, F, I, P],
+        "morec_layernorm_fwd": [P, P, P, I, P, P, P, P, P, I, I, F, I, F, F, U, U, U, P],
+        "morec_layernorm_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, F, F, U, U, U, P],
+        "morec_attn_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, F, F, I, F, U, U, P],
+        "morec_attn_bwd": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, F, I, F, U, U, P],
+        "morec_inbatch_mask": [P, P, P, P, I, I, I, P],
+        "morec_inbatch_ce_num_tiles": [I, I],
+        "morec_inbatch_ce_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P, P, P, P],
+        "morec_inbatch_ce_dlogits": [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, I, P],
+        "morec_bert_embed_fwd": [P, P, P, P, P, P, I, I, I, P],
+        "morec_bert_embed_bwd": [P, P, P, P, P, I, I, I, P],
+        "morec_gather_rows": [P, P, P, I, I, I, I, I, I, P],
+        "morec_scatter_add_rows": [P, P, P, I, I, I, I, I, P],
+        "morec_colsum": [P, P, I, I, I, I, P],
+        "morec_act_bwd": [P, P, P, L, I, I, P],
+        "morec_cast_f32_to_bf16": [P, P, L, P],
+        "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
+        "morec_clock_probe": [P, P],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
     _lib = lib
     return lib
 
@@ -116,14 +141,16 @@ class _timed_gemm:
 
 
 def _ptr(t):
+    """raw device address (argtypes convert the int); None -> NULL"""
     if t is None:
-        return c_void_p(0)
-    assert t.is_cuda, "morec_b200 kernels take device tensors only"
-    return c_void_p(t.data_ptr())
+        return None
+    if not t.is_cuda:
+        raise MorecError("morec_b200 kernels take device tensors only (no CPU fallback)")
+    return t.data_ptr()
 
 
 def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 # fp32-storage GEMM precision: True -> error-compensated 3xTF32 ("fp32" parity mode, C-ABI dtype 2),
@@ -175,9 +202,9 @@ def gemm(A, B, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, ldaux
     assert gemm_dtype_code(B) == dt
     out_bf16 = 1 if C.dtype == torch.bfloat16 else 0
     with _timed_gemm(2.0 * M * N * K):
-        rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), c_int(M), c_int(N), c_int(K),
-                            c_int(lda), c_int(ldb), c_int(ldc), c_int(ldaux), c_int(int(a_mn)), c_int(int(b_mn)),
-                            c_int(dt), c_int(out_bf16), c_int(epilogue), c_float(alpha), c_int(int(accumulate)), _stream())
+        rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), M, N, K,
+                            lda, ldb, ldc, ldaux, int(a_mn), int(b_mn),
+                            dt, out_bf16, epilogue, alpha, int(accumulate), _stream())
     _check(rc, "morec_gemm")
 
 
@@ -219,7 +246,7 @@ def linear_wgrad(dy, x, dw):
 # thin wrappers over the remaining entry points (device tensors in, pre-allocated outputs)
 # ------------------------------------------------------------------------------------------------
 def _u64(x):
-    return c_uint64(int(x) & 0xFFFFFFFFFFFFFFFF)
+    return int(x) & 0xFFFFFFFFFFFFFFFF
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, residual=None, pos=None, pos_period=0, p_pre=0.0, p_post=0.0, seed=0,
@@ -229,9 +256,9 @@ def layernorm_fwd(x, gamma, beta, eps, *, residual=None, pos=None, pos_period=0,
     y = out if out is not None else torch.empty_like(x)
     y_pre = torch.empty_like(x) if p_post > 0 else None
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-    rc = load().morec_layernorm_fwd(_ptr(x), _ptr(residual), _ptr(pos), c_int(pos_period), _ptr(gamma), _ptr(beta),
-                                    _ptr(y), _ptr(y_pre), _ptr(rstd), c_int(M), c_int(H), c_float(eps),
-                                    c_int(dtype_code(x)), c_float(p_pre), c_float(p_post), _u64(seed), _u64(off_pre),
+    rc = load().morec_layernorm_fwd(_ptr(x), _ptr(residual), _ptr(pos), pos_period, _ptr(gamma), _ptr(beta),
+                                    _ptr(y), _ptr(y_pre), _ptr(rstd), M, H, eps,
+                                    dtype_code(x), p_pre, p_post, _u64(seed), _u64(off_pre),
                                     _u64(off_post), _stream())
     _check(rc, "morec_layernorm_fwd")
     return y, y_pre, rstd
@@ -244,8 +271,8 @@ def layernorm_bwd(dy, y, gamma, beta, rstd, *, dy2=None, dgamma, dbeta, dbias=No
     dz = torch.empty_like(dy)
     dxb = torch.empty_like(dy) if p_pre > 0 else None
     rc = load().morec_layernorm_bwd(_ptr(dy), _ptr(dy2), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(rstd), _ptr(dz),
-                                    _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(dpos), c_int(pos_period),
-                                    c_int(M), c_int(H), c_int(dtype_code(dy)), c_float(p_pre), c_float(p_post),
+                                    _ptr(dxb), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(dpos), pos_period,
+                                    M, H, dtype_code(dy), p_pre, p_post,
                                     _u64(seed), _u64(off_pre), _u64(off_post), _stream())
     _check(rc, "morec_layernorm_bwd")
     return dz, (dxb if dxb is not None else dz)
@@ -254,9 +281,9 @@ def layernorm_bwd(dy, y, gamma, beta, rstd, *, dy2=None, dgamma, dbeta, dbias=No
 def attn_fwd(q, k, v, o, *, cu_seqlens=None, key_mask=None, causal=False, n_seq, seqlen, n_heads, head_dim, scale,
              masked_add=-1e9, dropout_p=0.0, seed=0, offset=0):
     assert q.stride(0) == k.stride(0) == v.stride(0)
-    rc = load().morec_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(key_mask), c_int(int(causal)),
-                               c_int(n_seq), c_int(seqlen), c_int(n_heads), c_int(head_dim), c_int(q.stride(0)),
-                               c_int(o.stride(0)), c_float(scale), c_float(masked_add), c_int(dtype_code(q)), c_float(dropout_p), _u64(seed),
+    rc = load().morec_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(key_mask), int(causal),
+                               n_seq, seqlen, n_heads, head_dim, q.stride(0),
+                               o.stride(0), scale, masked_add, dtype_code(q), dropout_p, _u64(seed),
                                _u64(offset), _stream())
     _check(rc, "morec_attn_fwd")
     return o
@@ -266,9 +293,9 @@ def attn_bwd(q, k, v, do, dq, dk, dv, *, cu_seqlens=None, key_mask=None, causal=
              head_dim, scale, masked_add=-1e9, dropout_p=0.0, seed=0, offset=0):
     assert q.stride(0) == k.stride(0) == v.stride(0) == dq.stride(0) == dk.stride(0) == dv.stride(0)
     rc = load().morec_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(cu_seqlens),
-                               _ptr(key_mask), c_int(int(causal)), c_int(n_seq), c_int(seqlen), c_int(n_heads),
-                               c_int(head_dim), c_int(q.stride(0)), c_int(do.stride(0)), c_float(scale), c_float(masked_add),
-                               c_int(dtype_code(q)), c_float(dropout_p), _u64(seed), _u64(offset), _stream())
+                               _ptr(key_mask), int(causal), n_seq, seqlen, n_heads,
+                               head_dim, q.stride(0), do.stride(0), scale, masked_add,
+                               dtype_code(q), dropout_p, _u64(seed), _u64(offset), _stream())
     _check(rc, "morec_attn_bwd")
 
 
@@ -277,7 +304,7 @@ def inbatch_mask(row_ids, col_ids, B, L):
     Wc = (C + 31) // 32
     member = torch.empty(B, Wc, device=row_ids.device, dtype=torch.int32)
     pad = torch.empty(Wc, device=row_ids.device, dtype=torch.int32)
-    rc = load().morec_inbatch_mask(_ptr(row_ids), _ptr(col_ids), _ptr(member), _ptr(pad), c_int(B), c_int(L), c_int(C),
+    rc = load().morec_inbatch_mask(_ptr(row_ids), _ptr(col_ids), _ptr(member), _ptr(pad), B, L, C,
                                    _stream())
     _check(rc, "morec_inbatch_mask")
     return member, pad
@@ -286,7 +313,7 @@ def inbatch_mask(row_ids, col_ids, B, L):
 def inbatch_ce_fwd(P, E, member, pad, log_pop, log_mask, B, L, col_offset=0, want_loss=True):
     R, D = P.shape
     C = E.shape[0]
-    NT = load().morec_inbatch_ce_num_tiles(c_int(C), c_int(gemm_dtype_code(P)))
+    NT = load().morec_inbatch_ce_num_tiles(C, gemm_dtype_code(P))
     dev = P.device
     part = torch.empty(2, R, NT, device=dev, dtype=torch.float32)
     tgt = torch.empty(R, device=dev, dtype=torch.float32)
@@ -294,8 +321,8 @@ def inbatch_ce_fwd(P, E, member, pad, log_pop, log_mask, B, L, col_offset=0, wan
     row_loss = torch.empty(R, device=dev, dtype=torch.float32)
     sum_cnt = torch.empty(2, device=dev, dtype=torch.float32)
     loss = torch.empty((), device=dev, dtype=torch.float32) if want_loss else None
-    rc = load().morec_inbatch_ce_fwd(_ptr(P), _ptr(E), _ptr(member), _ptr(pad), _ptr(log_pop), _ptr(log_mask), c_int(B),
-                                     c_int(L), c_int(D), c_int(C), c_int(col_offset), c_int(gemm_dtype_code(P)),
+    rc = load().morec_inbatch_ce_fwd(_ptr(P), _ptr(E), _ptr(member), _ptr(pad), _ptr(log_pop), _ptr(log_mask), B,
+                                     L, D, C, col_offset, gemm_dtype_code(P),
                                      _ptr(part[0]), _ptr(part[1]), _ptr(tgt), _ptr(row_lse), _ptr(row_loss),
                                      _ptr(sum_cnt), _ptr(loss), _stream())
     _check(rc, "morec_inbatch_ce_fwd")
@@ -309,24 +336,24 @@ def inbatch_ce_dlogits(P, E, member, pad, log_pop, log_mask, row_lse, grad_out, 
     ld = (C + align - 1) // align * align
     dS = torch.empty(R, ld, device=P.device, dtype=P.dtype)
     rc = load().morec_inbatch_ce_dlogits(_ptr(P), _ptr(E), _ptr(member), _ptr(pad), _ptr(log_pop), _ptr(log_mask),
-                                         _ptr(row_lse), _ptr(grad_out), _ptr(n_valid), c_int(B), c_int(L), c_int(D),
-                                         c_int(C), c_int(col_offset), c_int(gemm_dtype_code(P)), _ptr(dS), c_int(ld), _stream())
+                                         _ptr(row_lse), _ptr(grad_out), _ptr(n_valid), B, L, D,
+                                         C, col_offset, gemm_dtype_code(P), _ptr(dS), ld, _stream())
     _check(rc, "morec_inbatch_ce_dlogits")
     return dS[:, :C]
 
 
 def bert_embed_fwd(ids, pos, word, posemb, type0, out):
     n_tok, H = out.shape
-    rc = load().morec_bert_embed_fwd(_ptr(ids), _ptr(pos), _ptr(word), _ptr(posemb), _ptr(type0), _ptr(out), c_int(n_tok),
-                                     c_int(H), c_int(dtype_code(out)), _stream())
+    rc = load().morec_bert_embed_fwd(_ptr(ids), _ptr(pos), _ptr(word), _ptr(posemb), _ptr(type0), _ptr(out), n_tok,
+                                     H, dtype_code(out), _stream())
     _check(rc, "morec_bert_embed_fwd")
     return out
 
 
 def bert_embed_bwd(dz, ids, pos, dword, dposemb):
     n_tok, H = dz.shape
-    rc = load().morec_bert_embed_bwd(_ptr(dz), _ptr(ids), _ptr(pos), _ptr(dword), _ptr(dposemb), c_int(n_tok), c_int(H),
-                                     c_int(dtype_code(dz)), _stream())
+    rc = load().morec_bert_embed_bwd(_ptr(dz), _ptr(ids), _ptr(pos), _ptr(dword), _ptr(dposemb), n_tok, H,
+                                     dtype_code(dz), _stream())
     _check(rc, "morec_bert_embed_bwd")
 
 
@@ -335,8 +362,8 @@ def gather_rows(src, idx, out=None, out_dtype=None):
     H = src.shape[1]
     if out is None:
         out = torch.empty(n, H, device=src.device, dtype=out_dtype or src.dtype)
-    rc = load().morec_gather_rows(_ptr(src), _ptr(idx), _ptr(out), c_int(n), c_int(H), c_int(src.stride(0)),
-                                  c_int(out.stride(0)), c_int(dtype_code(src)), c_int(dtype_code(out)), _stream())
+    rc = load().morec_gather_rows(_ptr(src), _ptr(idx), _ptr(out), n, H, src.stride(0),
+                                  out.stride(0), dtype_code(src), dtype_code(out), _stream())
     _check(rc, "morec_gather_rows")
     return out
 
@@ -344,15 +371,15 @@ def gather_rows(src, idx, out=None, out_dtype=None):
 def scatter_add_rows(src, idx, dst):
     n, H = src.shape
     assert dst.dtype == torch.float32
-    rc = load().morec_scatter_add_rows(_ptr(src), _ptr(idx), _ptr(dst), c_int(n), c_int(H), c_int(src.stride(0)),
-                                       c_int(dst.stride(0)), c_int(dtype_code(src)), _stream())
+    rc = load().morec_scatter_add_rows(_ptr(src), _ptr(idx), _ptr(dst), n, H, src.stride(0),
+                                       dst.stride(0), dtype_code(src), _stream())
     _check(rc, "morec_scatter_add_rows")
     return dst
 
 
 def colsum(x, out):
     M, N = x.shape
-    rc = load().morec_colsum(_ptr(x), _ptr(out), c_int(M), c_int(N), c_int(x.stride(0)), c_int(dtype_code(x)), _stream())
+    rc = load().morec_colsum(_ptr(x), _ptr(out), M, N, x.stride(0), dtype_code(x), _stream())
     _check(rc, "morec_colsum")
     return out
 
@@ -361,24 +388,40 @@ def act_bwd(dy, aux, mode, out=None):
     """out = dy * act'(aux); mode 0: erf-GELU (aux = pre-activation), 1: ReLU (aux = activation output)"""
     out = out if out is not None else torch.empty_like(dy)
     assert dy.is_contiguous() and aux.is_contiguous()
-    rc = load().morec_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), c_int64(dy.numel()), c_int(mode), c_int(dtype_code(dy)),
+    rc = load().morec_act_bwd(_ptr(dy), _ptr(aux), _ptr(out), dy.numel(), mode, dtype_code(dy),
                               _stream())
     _check(rc, "morec_act_bwd")
     return out
 
 
 def cast_f32_to_bf16(src, dst):
-    rc = load().morec_cast_f32_to_bf16(_ptr(src), _ptr(dst), c_int64(src.numel()), _stream())
+    rc = load().morec_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream())
     _check(rc, "morec_cast_f32_to_bf16")
     return dst
 
 
-class AdamChunk(ctypes.Structure):
+class AdamTensor(ctypes.Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p_bf16", c_void_p),
                 ("n", c_int), ("lr", c_float), ("wd", c_float)]
 
 
-def adamw_multi(chunks_dev, n_chunks, beta1, beta2, eps, step, inv_scale=None, found_inf=None, check_finite=False):
-    rc = load().morec_adamw_multi(_ptr(chunks_dev), c_int(n_chunks), c_float(beta1), c_float(beta2), c_float(eps),
-                                  c_int(step), _ptr(inv_scale), _ptr(found_inf), c_int(int(check_finite)), _stream())
+AdamChunk = AdamTensor   # layout check in tests
+
+
+def adamw_chunk_elems():
+    h = load()
+    h.morec_adamw_chunk_elems.restype = c_int
+    return h.morec_adamw_chunk_elems()
+
+
+def adamw_multi(table_dev, chunk_start_dev, n_tensors, n_chunks, beta1, beta2, eps, step, inv_scale=None,
+                found_inf=None, check_finite=False):
+    rc = load().morec_adamw_multi(_ptr(table_dev), _ptr(chunk_start_dev), n_tensors, n_chunks, beta1, beta2, eps, step,
+                                  _ptr(inv_scale), _ptr(found_inf), int(check_finite), _stream())
     _check(rc, "morec_adamw_multi")
+
+
+def clock_probe(out):
+    """out: int64[2] device tensor <- (SM cycles, ns) of a ~20 us spin on the current stream"""
+    rc = load().morec_clock_probe(_ptr(out), _stream())
+    _check(rc, "morec_clock_probe")

@@ -1,6 +1,7 @@
 """User / item encoders, mirroring inbatch_sasrec_e2e_text/model/encoders.py on the morec_b200 CUDA kernels."""
 import itertools
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.nn.init import xavier_normal_, constant_
@@ -34,6 +35,14 @@ class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
                                                       n_heads=num_attention_heads, dropout=dropout, n_layers=n_layers)
         self.apply(self._init_weights)
         self.compute_dtype = "fp32"
+        self._qkv_groups = None
+
+    def _fused_qkv(self):
+        if self._qkv_groups is None:
+            self._qkv_groups = [ops.FusedParamGroup([b.multi_head_attention.w_Q.weight, b.multi_head_attention.w_K.weight,
+                                                     b.multi_head_attention.w_V.weight])
+                                for b in self.transformer_encoder.transformer_blocks]
+        return [g.buffer() for g in self._qkv_groups]
 
     def _init_weights(self, module):                # reference: encoders.py:14-21
         if isinstance(module, nn.Embedding):
@@ -50,7 +59,8 @@ class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
         B, L, D = input_embs.shape
         adt = _adt(self)
         drop = _drop_ctx(self.training, te.dropout_p, te.dropout_p)
-        meta = dict(n_blocks=len(te.transformer_blocks), n_heads=te.n_heads, L=L, adt=adt, drop=drop, x3=_x3(self))
+        meta = dict(n_blocks=len(te.transformer_blocks), n_heads=te.n_heads, L=L, adt=adt, drop=drop, x3=_x3(self),
+                    wqkv=self._fused_qkv())
         X = input_embs.reshape(B * L, D)
         if X.dtype != adt:
             X = X.to(adt)
@@ -69,6 +79,16 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         self.bert_model = bert_model
         self.fc = nn.Linear(word_embedding_dim, item_embedding_dim)
         self.compute_dtype = "fp32"
+        self._qkv_groups = None
+
+    def _fused_qkv(self):
+        if self._qkv_groups is None:
+            self._qkv_groups = [(ops.FusedParamGroup([l.attention.self.query.weight, l.attention.self.key.weight,
+                                                      l.attention.self.value.weight]),
+                                 ops.FusedParamGroup([l.attention.self.query.bias, l.attention.self.key.bias,
+                                                      l.attention.self.value.bias]))
+                                for l in self.bert_model.encoder.layer]
+        return [w.buffer() for w, _ in self._qkv_groups], [b.buffer() for _, b in self._qkv_groups]
 
     def _flat_params(self):
         bm = self.bert_model
@@ -89,33 +109,36 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         n, two_t = text.shape
         T = two_t // 2
         cfg = self.bert_model.config
-        ids = text[:, :T]
-        am = text[:, T:] != 0
-        lens = am.sum(dim=1)
-        keep = lens > 0
         adt = _adt(self)
         D = self.fc.weight.shape[0]
-        n_enc = int(keep.sum())                     # one D2H sync per call (sizes of the packed buffers)
+        dev = text.device
+        # ---- packing plan: ONE device->host round trip (the attention mask, n*T bytes), index arithmetic in numpy
+        am = (text[:, T:] != 0).cpu().numpy()                       # the step's only size-determining sync
+        lens = am.sum(axis=1)
+        enc_rows = np.nonzero(lens > 0)[0]
+        n_enc = int(enc_rows.size)
         if n_enc == 0:
-            return torch.zeros(n, D, device=text.device, dtype=adt)
-        enc_rows = torch.nonzero(keep).squeeze(1)
-        am_e = am[enc_rows]
-        ids_e = ids[enc_rows]
-        lens_e = lens[enc_rows]
-        cu = torch.zeros(n_enc + 1, device=text.device, dtype=torch.int32)
-        cu[1:] = torch.cumsum(lens_e, 0).to(torch.int32)
-        tok_ids = ids_e[am_e].to(torch.int64).contiguous()
-        tok_pos = torch.arange(T, device=text.device, dtype=torch.int32).view(1, T).expand(n_enc, T)[am_e].contiguous()
+            return torch.zeros(n, D, device=dev, dtype=adt)
+        r, c = np.nonzero(am[enc_rows])                             # row-major: tokens of one item stay contiguous
+        src = enc_rows[r].astype(np.int64) * two_t + c              # flat index of every kept word piece in `text`
+        cu_np = np.zeros(n_enc + 1, dtype=np.int32)
+        np.cumsum(lens[enc_rows], out=cu_np[1:])
+        plan = torch.from_numpy(np.concatenate([src, c.astype(np.int64), cu_np.astype(np.int64)])).to(dev, non_blocking=True)
+        n_tok = int(src.size)
+        tok_ids = text.reshape(-1)[plan[:n_tok]].to(torch.int64).contiguous()
+        tok_pos = plan[n_tok:2 * n_tok].to(torch.int32)
+        cu = plan[2 * n_tok:].to(torch.int32)
         cls_rows = cu[:-1].contiguous()
         drop = _drop_ctx(self.training, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
         meta = dict(n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps, max_len=T,
                     adt=adt, drop=drop, x3=_x3(self))
+        meta["wqkv"], meta["bqkv"] = self._fused_qkv()
         E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *self._flat_params())
         if n_enc == n:
             return E
-        slot2enc = torch.full((n,), -1, device=text.device, dtype=torch.int32)
-        slot2enc[enc_rows] = torch.arange(n_enc, device=text.device, dtype=torch.int32)
-        return ops.GatherRowsFn.apply(E, slot2enc, adt)
+        s2e = np.full(n, -1, dtype=np.int32)
+        s2e[enc_rows] = np.arange(n_enc, dtype=np.int32)
+        return ops.GatherRowsFn.apply(E, torch.from_numpy(s2e).to(dev, non_blocking=True), adt)
 
 
 class Bert_Encoder(torch.nn.Module):                # reference: encoders.py:73-117

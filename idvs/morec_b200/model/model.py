@@ -20,7 +20,7 @@ class _IdEmbedding(nn.Embedding):
         # pad slots provably receive an exactly-zero gradient, which matches padding_idx=0 semantics.
         shape = ids.shape
         idx = ids.reshape(-1).to(torch.int32).contiguous()
-        out = ops.GatherRowsFn.apply(self.weight, idx, self.weight.dtype)
+        out = ops.GatherRowsFn.apply(self.weight, idx, getattr(self, "out_dtype", self.weight.dtype))
         return out.view(*shape, self.weight.shape[1])
 
 
@@ -53,6 +53,8 @@ class Model(torch.nn.Module):
         self.user_encoder.compute_dtype = name
         if self.use_modal:
             self.bert_encoder.text_encoders['title'].compute_dtype = name
+        else:
+            self.id_embedding.out_dtype = torch.bfloat16 if name == "bf16" else torch.float32
 
     # -------------------------------------------------------------------------------------------
     def _encode_items(self, ids_flat, sample_items):
@@ -84,8 +86,12 @@ class Model(torch.nn.Module):
         log_pop_c = self._log_pop[ids_flat].contiguous()                  # model.py:32-33
         score_embs = self._encode_items(ids_flat, sample_items)          # [C, D]   model.py:34-37
         # input_embs[:, :-1]  (model.py:39-41)
-        in_rows = (torch.arange(B, device=dev, dtype=torch.int32).view(B, 1) * (L + 1)
-                   + torch.arange(L, device=dev, dtype=torch.int32).view(1, L)).reshape(-1).contiguous()
+        key = (B, L, str(dev))
+        if getattr(self, "_in_rows_key", None) != key:
+            self._in_rows = (torch.arange(B, device=dev, dtype=torch.int32).view(B, 1) * (L + 1)
+                             + torch.arange(L, device=dev, dtype=torch.int32).view(1, L)).reshape(-1).contiguous()
+            self._in_rows_key = key
+        in_rows = self._in_rows
         X = ops.GatherRowsFn.apply(score_embs, in_rows, score_embs.dtype)
         prec_vec = self.user_encoder(X.view(B, L, D), log_mask, local_rank).reshape(B * L, D)
         # in-batch debiased CE (model.py:45-67)

@@ -67,6 +67,60 @@ def _z32(p):
     return torch.zeros(p.shape, device=p.device, dtype=torch.float32)
 
 
+class _Arena:
+    """one zero-filled fp32 buffer per backward pass from which every parameter gradient is carved (a single memset
+    instead of ~180 fill kernels; 16-byte aligned slices so they can be TMA reduce-add targets)"""
+
+    def __init__(self, dev, shapes):
+        self.total = sum((math.prod(sh) + 3) // 4 * 4 for sh in shapes)
+        self.buf = torch.zeros(max(self.total, 4), device=dev, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, shape):
+        n = math.prod(shape)
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 3) // 4 * 4
+        assert self.off <= self.buf.numel()
+        return v
+
+
+class FusedParamGroup:
+    """Keeps several nn.Parameters (e.g. the Q, K, V projection weights) as consecutive row blocks of ONE contiguous
+    buffer by re-pointing their .data, so the fused [3H, H] projection weight exists without a per-step concat.
+    The Parameter objects, their names, order and values are unchanged; if something re-allocates
+    the parameters (.to(), load_state_dict copies in place so that is fine) the group is rebuilt lazily."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.buf = None
+
+    def _valid(self):
+        if self.buf is None:
+            return False
+        off = 0
+        base = self.buf.data_ptr()
+        for p in self.params:
+            if p.data_ptr() != base + 4 * off or p.device != self.buf.device:
+                return False
+            off += p.numel()
+        return True
+
+    @torch.no_grad()
+    def buffer(self):
+        if not self._valid():
+            p0 = self.params[0]
+            cols = p0.shape[1:] if p0.dim() > 1 else ()
+            rows = sum(p.shape[0] for p in self.params)
+            buf = torch.empty((rows,) + tuple(cols), device=p0.device, dtype=torch.float32)
+            r = 0
+            for p in self.params:
+                buf[r:r + p.shape[0]].copy_(p.data)
+                p.data = buf[r:r + p.shape[0]]
+                r += p.shape[0]
+            self.buf = buf
+        return self.buf
+
+
 def _dgrad_acc(dy, w, into):
     """into += dy @ w"""
     if into.dtype == torch.float32:
@@ -110,32 +164,33 @@ class BertTowerFn(torch.autograd.Function):
         layers = []
         for l in range(n_layers):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
-            wqkv = _cw(torch.cat([qw.detach(), kw.detach(), vw.detach()], dim=0), adt)
-            bqkv = torch.cat([qb.detach(), kb.detach(), vb.detach()], dim=0)
+            wqkv, bqkv = _cw(meta["wqkv"][l], adt), meta["bqkv"][l]      # fused [3H, H] / [3H] (FusedParamGroup)
+            w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
             qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
             ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
             lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq,
                          seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn,
                          seed=drop.seed, offset=drop.off(1 + 4 * l))
-            ao = lib.linear_fwd(ctxo, _cw(aow, adt), aob.detach())
+            ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
             x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
                                              seed=drop.seed, off_pre=drop.off(2 + 4 * l))
             del ao
             pre = torch.empty(n_tok, iw.shape[0], device=dev, dtype=adt)
-            act = lib.linear_fwd(x1, _cw(iw, adt), ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
-            fo = lib.linear_fwd(act, _cw(ow, adt), ob.detach())
+            act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
+            fo = lib.linear_fwd(act, w_o, ob.detach())
             x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
                                              seed=drop.seed, off_pre=drop.off(3 + 4 * l))
             del fo
-            layers.append([x, qkv, ctxo, x1, rstd1, pre, act, rstd2])
+            layers.append([x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o)])
             x = x2
         # ---- CLS pooling + fc + GELU
         cls = lib.gather_rows(x, cls_rows)                                # [n_seq, H]
         D = fc_w.shape[0]
         fc_pre = torch.empty(n_seq, D, device=dev, dtype=adt)
-        E = lib.linear_fwd(cls, _cw(fc_w, adt), fc_b.detach(), epilogue=lib.EPI_GELU, pre=fc_pre)
+        w_fc = _cw(fc_w, adt)
+        E = lib.linear_fwd(cls, w_fc, fc_b.detach(), epilogue=lib.EPI_GELU, pre=fc_pre)
         ctx.meta = meta
-        ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre)
+        ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre, w_fc=w_fc)
         ctx.idx = (tok_ids, tok_pos, cu_seqlens, cls_rows)
         ctx.params = params
         return E
@@ -158,15 +213,17 @@ class BertTowerFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(dh)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dE = dE.contiguous().to(adt)
+        arena = _Arena(dev, [p.shape for p in params] + [(H,)])
+        _z = lambda p: arena.take(p.shape)   # noqa: E731  zero-initialised gradient slice
         # ---- fc + GELU backward
         cls, fc_pre = saved["cls"], saved["fc_pre"]
         dpre = lib.act_bwd(dE, fc_pre, 0)
-        g_fcw = _z32(fc_w)
+        g_fcw = _z(fc_w)
         lib.linear_wgrad(dpre, cls, g_fcw)
-        g_fcb = torch.zeros(fc_w.shape[0], device=dev, dtype=torch.float32)
+        g_fcb = _z(fc_b)
         lib.colsum(dpre, g_fcb)
         grads[-2], grads[-1] = (g_fcw if need[-2] else None), (g_fcb if need[-1] else None)
-        dcls = lib.linear_dgrad(dpre, _cw(fc_w, adt))
+        dcls = lib.linear_dgrad(dpre, saved["w_fc"])
         # ---- scatter CLS grads into the gradient of the last hidden state
         dx32 = torch.zeros(n_tok, H, device=dev, dtype=torch.float32)
         lib.scatter_add_rows(dcls, cls_rows, dx32)
@@ -175,32 +232,34 @@ class BertTowerFn(torch.autograd.Function):
         x_out = saved["x_last"]
         for l in reversed(range(n_layers)):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
-            x, qkv, ctxo, x1, rstd1, pre, act, rstd2 = saved["layers"][l]
+            x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o) = saved["layers"][l]
             base = 5 + 16 * l
+            # gradients of the three projection weights / biases are row blocks of one fused buffer
+            dwqkv, dbqkv = arena.take((3 * H, H)), arena.take((3 * H,))
             # output LayerNorm (y = x_out)
-            dg2, db2, dob = _z32(g2), _z32(b2), _z32(ob)
+            dg2, db2, dob = _z(g2), _z(b2), _z(ob)
             dz2, dfo = lib.layernorm_bwd(dx, x_out, g2.detach(), b2.detach(), rstd2, dgamma=dg2, dbeta=db2, dbias=dob,
                                          p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(3 + 4 * l))
             del dx
             # FFN2 / FFN1
-            dow = _z32(ow)
+            dow = _z(ow)
             lib.linear_wgrad(dfo, act, dow)
-            dpre_i = lib.linear_dgrad(dfo, _cw(ow, adt), epilogue=lib.EPI_MUL_GELU_GRAD, aux=pre)
+            dpre_i = lib.linear_dgrad(dfo, w_o, epilogue=lib.EPI_MUL_GELU_GRAD, aux=pre)
             if dfo is not dz2:
                 del dfo
-            dib, diw = _z32(ib), _z32(iw)
+            dib, diw = _z(ib), _z(iw)
             lib.colsum(dpre_i, dib)
             lib.linear_wgrad(dpre_i, x1, diw)
-            dx1_b = lib.linear_dgrad(dpre_i, _cw(iw, adt))
+            dx1_b = lib.linear_dgrad(dpre_i, w_i)
             del dpre_i
             # attention-output LayerNorm: dy = dz2 + dx1_b, y = x1
-            dg1, db1, daob = _z32(g1), _z32(b1), _z32(aob)
+            dg1, db1, daob = _z(g1), _z(b1), _z(aob)
             dz1, dao = lib.layernorm_bwd(dz2, x1, g1.detach(), b1.detach(), rstd1, dy2=dx1_b, dgamma=dg1, dbeta=db1,
                                          dbias=daob, p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(2 + 4 * l))
             del dz2, dx1_b
-            daow = _z32(aow)
+            daow = _z(aow)
             lib.linear_wgrad(dao, ctxo, daow)
-            dctx = lib.linear_dgrad(dao, _cw(aow, adt))
+            dctx = lib.linear_dgrad(dao, w_ao)
             if dao is not dz1:
                 del dao
             # attention core
@@ -210,12 +269,9 @@ class BertTowerFn(torch.autograd.Function):
                          dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
             del dctx
             # fused QKV projection backward
-            wqkv32 = torch.cat([qw.detach(), kw.detach(), vw.detach()], dim=0)
-            dwqkv = torch.zeros_like(wqkv32)
             lib.linear_wgrad(dqkv, x, dwqkv)
-            dbqkv = torch.zeros(3 * H, device=dev, dtype=torch.float32)
             lib.colsum(dqkv, dbqkv)
-            dx = _dgrad_acc(dqkv, _cw(wqkv32, adt), dz1)
+            dx = _dgrad_acc(dqkv, wqkv, dz1)
             del dqkv, dz1
             x_out = x
             lay = (dwqkv[:H], dbqkv[:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:],
@@ -225,17 +281,17 @@ class BertTowerFn(torch.autograd.Function):
             saved["layers"][l] = None
         # ---- embeddings backward: y = dropout(LN(z)), z = word + pos + type
         y_emb, rstd0 = saved["emb"]
-        deg, deb = _z32(eg), _z32(eb)
-        dtype_sum = torch.zeros(H, device=dev, dtype=torch.float32)
+        deg, deb = _z(eg), _z(eb)
+        dtype_sum = arena.take((H,))
         dz0, _ = lib.layernorm_bwd(dx, y_emb, eg.detach(), eb.detach(), rstd0, dgamma=deg, dbeta=deb, dbias=dtype_sum,
                                    p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
-        dword = _z32(word) if need[0] else None
-        dposw = _z32(posw) if need[1] else None
+        dword = _z(word) if need[0] else None
+        dposw = _z(posw) if need[1] else None
         if dword is not None or dposw is not None:
             lib.bert_embed_bwd(dz0, tok_ids, tok_pos, dword, dposw)
         dtypew = None
         if need[2]:
-            dtypew = _z32(typew)
+            dtypew = _z(typew)
             dtypew[0].copy_(dtype_sum)
         grads[0], grads[1], grads[2] = dword, dposw, dtypew
         grads[3] = deg if need[3] else None
@@ -292,20 +348,21 @@ class SasrecFn(torch.autograd.Function):
         blocks = []
         for l in range(n_blocks):
             (wq, wk, wv, fc, g1, b1, w1, bb1, w2, bb2, g2, b2) = params[3 + 12 * l: 3 + 12 * (l + 1)]
-            wqkv = _cw(torch.cat([wq.detach(), wk.detach(), wv.detach()], dim=0), adt)
+            wqkv = _cw(meta["wqkv"][l], adt)                            # fused [3D, D] (FusedParamGroup)
+            w_fc, w_1, w_2 = _cw(fc, adt), _cw(w1, adt), _cw(w2, adt)
             qkv = lib.linear_fwd(h, wqkv)
             ctxo = torch.empty(R, D, device=dev, dtype=adt)
             lib.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ctxo, key_mask=log_mask, causal=True, n_seq=B,
                          seqlen=L, n_heads=n_heads, head_dim=dk, scale=scale, masked_add=_MASKED_ADD,
                          dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
-            ao = lib.linear_fwd(ctxo, _cw(fc, adt))
+            ao = lib.linear_fwd(ctxo, w_fc)
             h1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), 1e-6, residual=h, p_pre=drop.p_hidden,
                                              seed=drop.seed, off_pre=drop.off(2 + 4 * l))
-            u = lib.linear_fwd(h1, _cw(w1, adt), bb1.detach(), epilogue=lib.EPI_RELU)
-            fo = lib.linear_fwd(u, _cw(w2, adt), bb2.detach())
+            u = lib.linear_fwd(h1, w_1, bb1.detach(), epilogue=lib.EPI_RELU)
+            fo = lib.linear_fwd(u, w_2, bb2.detach())
             h2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), 1e-6, residual=h1, p_pre=drop.p_hidden,
                                              seed=drop.seed, off_pre=drop.off(3 + 4 * l))
-            blocks.append([h, qkv, ctxo, h1, rstd1, u, rstd2])
+            blocks.append([h, qkv, ctxo, h1, rstd1, u, rstd2, (wqkv, w_fc, w_1, w_2)])
             h = h2
         ctx.meta = meta
         ctx.saved = dict(emb=emb_saved, blocks=blocks, h_last=h, log_mask=log_mask)
@@ -327,43 +384,44 @@ class SasrecFn(torch.autograd.Function):
         scale = 1.0 / (dk ** 0.5)
         dev = dx.device
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        arena = _Arena(dev, [p.shape for p in params])
+        _z = lambda p: arena.take(p.shape)   # noqa: E731
         h_out = saved["h_last"]
         for l in reversed(range(n_blocks)):
             (wq, wk, wv, fc, g1, b1, w1, bb1, w2, bb2, g2, b2) = params[3 + 12 * l: 3 + 12 * (l + 1)]
-            h, qkv, ctxo, h1, rstd1, u, rstd2 = saved["blocks"][l]
+            h, qkv, ctxo, h1, rstd1, u, rstd2, (wqkv, w_fc, w_1, w_2) = saved["blocks"][l]
             base = 3 + 12 * l
-            dg2, db2, dbb2 = _z32(g2), _z32(b2), _z32(bb2)
+            dwqkv = arena.take((3 * D, D))
+            dg2, db2, dbb2 = _z(g2), _z(b2), _z(bb2)
             dz2, dfo = lib.layernorm_bwd(dx, h_out, g2.detach(), b2.detach(), rstd2, dgamma=dg2, dbeta=db2, dbias=dbb2,
                                          p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(3 + 4 * l))
-            dw2 = _z32(w2)
+            dw2 = _z(w2)
             lib.linear_wgrad(dfo, u, dw2)
-            du = lib.linear_dgrad(dfo, _cw(w2, adt), epilogue=lib.EPI_MUL_RELU_GRAD, aux=u)
-            dbb1, dw1 = _z32(bb1), _z32(w1)
+            du = lib.linear_dgrad(dfo, w_2, epilogue=lib.EPI_MUL_RELU_GRAD, aux=u)
+            dbb1, dw1 = _z(bb1), _z(w1)
             lib.colsum(du, dbb1)
             lib.linear_wgrad(du, h1, dw1)
-            dh1_b = lib.linear_dgrad(du, _cw(w1, adt))
-            dg1, db1 = _z32(g1), _z32(b1)
+            dh1_b = lib.linear_dgrad(du, w_1)
+            dg1, db1 = _z(g1), _z(b1)
             dz1, dao = lib.layernorm_bwd(dz2, h1, g1.detach(), b1.detach(), rstd1, dy2=dh1_b, dgamma=dg1, dbeta=db1,
                                          p_pre=drop.p_hidden, seed=drop.seed, off_pre=drop.off(2 + 4 * l))
-            dfc = _z32(fc)
+            dfc = _z(fc)
             lib.linear_wgrad(dao, ctxo, dfc)
-            dctx = lib.linear_dgrad(dao, _cw(fc, adt))
+            dctx = lib.linear_dgrad(dao, w_fc)
             dqkv = torch.empty_like(qkv)
             lib.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                          key_mask=log_mask, causal=True, n_seq=B, seqlen=L, n_heads=n_heads, head_dim=dk, scale=scale,
                          masked_add=_MASKED_ADD, dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
-            wqkv32 = torch.cat([wq.detach(), wk.detach(), wv.detach()], dim=0)
-            dwqkv = torch.zeros_like(wqkv32)
             lib.linear_wgrad(dqkv, h, dwqkv)
-            dx = _dgrad_acc(dqkv, _cw(wqkv32, adt), dz1)
+            dx = _dgrad_acc(dqkv, wqkv, dz1)
             h_out = h
             lay = (dwqkv[:D], dwqkv[D:2 * D], dwqkv[2 * D:], dfc, dg1, db1, dw1, dbb1, dw2, dbb2, dg2, db2)
             for j, g in enumerate(lay):
                 grads[base + j] = g if need[base + j] else None
             saved["blocks"][l] = None
         y0, rstd0 = saved["emb"]
-        dg0, db0 = _z32(g0), _z32(b0)
-        dpos = _z32(posw)
+        dg0, db0 = _z(g0), _z(b0)
+        dpos = _z(posw)
         dX, _ = lib.layernorm_bwd(dx, y0, g0.detach(), b0.detach(), rstd0, dgamma=dg0, dbeta=db0, dpos=dpos,
                                   pos_period=L, p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
         # position table may be longer than L rows (it is exactly L in the reference, modules.py:82)

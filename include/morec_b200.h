@@ -140,13 +140,14 @@ int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mod
 int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* ---- multi-tensor AdamW with fused unscale + found-inf (run.py:159-162, 245-247) ---------------
- * chunks: DEVICE array of MorecAdamChunk (each <= 65536 elements of one parameter).  torch.optim.AdamW
- * semantics (decoupled weight decay, bias correction with `step` >= 1).  inv_scale (device scalar, may be null)
- * multiplies the gradients (GradScaler.unscale_); when check_finite != 0 found_inf (device scalar, must be zeroed
- * by the caller) is set to 1 if any gradient is inf/nan and the whole update is skipped.  p_bf16 (optional)
- * receives a bf16 copy of the updated parameter (fast-mode weights).
+ * tensors: DEVICE array of n_tensors MorecAdamTensor (one per parameter); chunk_start: DEVICE int32[n_tensors+1],
+ * exclusive prefix sum of ceil(n / morec_adamw_chunk_elems()) per tensor; n_chunks = chunk_start[n_tensors].
+ * torch.optim.AdamW semantics (decoupled weight decay, bias correction with `step` >= 1).  inv_scale (device
+ * scalar, may be null) multiplies the gradients (GradScaler.unscale_); when check_finite != 0 found_inf (device
+ * scalar, zeroed by the caller) is set to 1 if any gradient is inf/nan and the whole update is skipped.
+ * p_bf16 (optional) receives a bf16 copy of the updated parameter (bf16-mode weight shadows).
  */
-typedef struct MorecAdamChunk {
+typedef struct MorecAdamTensor {
     float* p;
     const float* g;
     float* m;
@@ -155,9 +156,15 @@ typedef struct MorecAdamChunk {
     int n;
     float lr;
     float wd;
-} MorecAdamChunk;
-int morec_adamw_multi(const void* chunks, int n_chunks, float beta1, float beta2, float eps, int step,
-                      const float* inv_scale, float* found_inf, int check_finite, void* stream);
+} MorecAdamTensor;
+int morec_adamw_chunk_elems(void);
+int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks, float beta1,
+                      float beta2, float eps, int step, const float* inv_scale, float* found_inf, int check_finite,
+                      void* stream);
+
+/* ---- SM clock probe: out[0] = SM cycles, out[1] = nanoseconds elapsed over a ~20 us spin of one thread; lets
+ * bench.py report the SM clock under load without NVML queries inside the timed region (they stall launches). */
+int morec_clock_probe(uint64_t* out_cycles_ns, void* stream);
 
 #ifdef __cplusplus
 }

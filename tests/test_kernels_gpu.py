@@ -20,7 +20,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("dt,x3,tol", [(torch.float32, True, 2e-5), (torch.float32, False, 2e-3), (torch.bfloat16, False, 1e-4)])
+@pytest.mark.parametrize("dt,x3,tol", [(torch.float32, True, 5e-5), (torch.float32, False, 2e-3), (torch.bfloat16, False, 1e-4)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
 def test_gemm_layouts(lib, dt, x3, tol, a_mn, b_mn):
     with lib.fp32_mode(x3):
@@ -32,7 +32,8 @@ def test_gemm_layouts(lib, dt, x3, tol, a_mn, b_mn):
             lib.gemm(A, B, C, M=M, N=N, K=K, lda=A.stride(0), ldb=B.stride(0), ldc=N, a_mn=a_mn, b_mn=b_mn)
             a = A.double().t() if a_mn else A.double()
             b = B.double().t() if b_mn else B.double()
-            assert rel(C, a @ b.t()) < tol, (M, N, K)
+            r = rel(C, a @ b.t())
+            assert r < tol, (M, N, K, r)
 
 
 def _epilogue_checks(lib, dt, tol):

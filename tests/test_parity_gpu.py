@@ -110,3 +110,50 @@ def test_training_mode_dropout_runs_and_is_finite(goldens):
                 assert torch.isfinite(p.grad).all(), n
     assert all(map(lambda v: v == v and abs(v) < 1e4, losses))
     assert losses[0] != losses[1]          # different dropout masks per call
+
+
+@pytest.mark.parametrize("mode,loss_tol,cos_min", [("tf32", 1e-2, 0.999), ("bf16", 5e-2, 0.99)])
+@pytest.mark.parametrize("name", ["id_cfg1_shape", "text_tiny"])
+def test_fast_modes_stay_close_to_reference(goldens, name, mode, loss_tol, cos_min):
+    """fast modes are NOT the parity mode: their measured deviation from the reference is bounded here and reported
+    in profiles/README.md (loss tolerance 1e-2 for tf32, 5e-2 for bf16; gradient direction cosine >= 0.999 / 0.99)."""
+    g = goldens[name]
+    model = build_model(g)
+    model.set_compute_dtype(mode)
+    loss, E, P, grads = run_cuda(model, g)
+    assert abs(loss - float(g["loss"])) <= loss_tol, (loss, float(g["loss"]))
+    num = den_a = den_b = 0.0
+    for k, gref in g["grads"].items():
+        if "pooler" in k:
+            continue
+        a, b = grads[k].double().reshape(-1), gref.double().reshape(-1)
+        num += float(a @ b); den_a += float(a @ a); den_b += float(b @ b)
+    cos = num / ((den_a ** 0.5) * (den_b ** 0.5) + 1e-30)
+    assert cos >= cos_min, cos
+
+
+def test_bert_base_shape_vs_oracle():
+    """BERT-base text tower (12 layers, H=768, T=30, D=512, L=25) on a 3-user batch vs the CPU oracle: the headline
+    architecture at a size the oracle finishes in seconds.  Parity mode, north-star tolerance 1e-3 on the loss and
+    on every logit-forming embedding."""
+    from transformers import BertConfig, BertModel
+    from oracle import morec_oracle as O
+    from idvs.morec_b200.model import Model
+    from idvs.morec_b200.synth import synth_batch
+    import bench
+    torch.manual_seed(5)
+    cfg = dict(bench.CFG)
+    B = 3
+    d = synth_batch(B, cfg["L"], 500, cfg["T"], seed=5, modal=True, n_users_pop=300)
+    bert = BertModel(BertConfig(**bench.BERT_BASE))
+    model = Model(bench.make_args(cfg), 500, True, bert, d["pop_prob"].numpy()).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    out = O.model_forward(sd, d["ids"], d["items"], d["log_mask"], d["pop_prob"], use_modal=True, n_heads_user=2, n_heads_bert=12)
+    model = model.cuda()
+    cap = {}
+    orig = model._encode_items
+    model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+    loss = model(d["ids"].reshape(-1).cuda(), d["items"].cuda(), d["log_mask"].cuda(), 0)
+    assert abs(float(loss) - float(out.loss)) <= 1e-3, (float(loss), float(out.loss))
+    nonpad = d["ids"].reshape(-1) != 0
+    assert float((cap["E"].detach().cpu().float()[nonpad] - out.score_embs[nonpad]).abs().max()) <= 1e-3
