@@ -177,7 +177,7 @@ def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
                        f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt
 
 
-def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0):
+def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global"):
     """model + optimizer + synthetic batches exactly as the reference loop builds them (run.py:127-162);
     returns (step_fn, pinned host batches, device-resident batches, H2D bytes per step)"""
     import torch
@@ -196,6 +196,8 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0):
     pop = batches[0]["pop_prob"].numpy()
     model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
     model.set_compute_dtype(mode)
+    model.item_dedup = "always"      # north star: "forward over the batch's unique items" (at every N)
+    model.parallel_mode = parallel
     model.train()
     if world > 1:
         from idvs.morec_b200.parallel import wrap_ddp
@@ -228,6 +230,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="morec", choices=["morec", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--parallel", default="global", choices=["global", "local"],
+                    help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-users", type=int, default=4)
     args = ap.parse_args()
@@ -262,7 +266,7 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
-    step, host, resident, h2d_bytes = setup_training(cfg, args.mode, W + K, rank, world, local_rank)
+    step, host, resident, h2d_bytes = setup_training(cfg, args.mode, W + K, rank, world, local_rank, args.parallel)
 
     def sync():
         if world > 1:
@@ -272,7 +276,7 @@ def main():
     # ---------------- device-resident throughput (`value`): K steps, batches already in HBM
     # warm-up: W steps, the first one on the batch with the most real tokens so the allocator reaches its
     # steady-state footprint before anything is timed
-    big = max(range(len(host)), key=lambda i: int((host[i][1][:, :, cfg["T"]:] != 0).sum()))
+    big = max(range(len(host)), key=lambda i: int((host[i][1].reshape(-1, 2 * cfg["T"])[:, cfg["T"]:] != 0).sum()))
     step(*resident[big])
     for i in range(W - 1):
         step(*resident[i])
@@ -359,10 +363,13 @@ def main():
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32 (3xTF32 tensor-core emulation)", "tf32": "tf32", "bf16": "bf16"}[args.mode],
             "data": "synthetic",
-            "config": {"workload": workload, "mode": args.mode, "parallelism": f"dp{world}",
+            "config": {"workload": workload, "mode": args.mode,
+                       "parallelism": f"dp{world}" + (f" ({args.parallel}: " + ("item embeddings all-gathered, global negatives, "
+                                      "reduce-scatter in backward + DDP grad all-reduce)" if args.parallel == "global"
+                                      else "reference DDP, rank-local negatives)") if world > 1 else ""),
                        "l2_policy": "every step uses a different batch and streams >10 GB of activations (>> 126 MB L2)",
                        "dropout": cfg["drop"], "optimizer": "FusedAdamW (2 groups)",
-                       "items_encoded": "non-pad slots only (pad slots are exact zeros in the loss); pad tokens skipped"},
+                       "items_encoded": "each distinct non-pad item of the (global) batch once; pad tokens skipped"},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
     print(json.dumps(line))

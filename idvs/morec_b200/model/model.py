@@ -25,6 +25,12 @@ class _IdEmbedding(nn.Embedding):
 
 
 class Model(torch.nn.Module):
+    # The scoring / CE block ALWAYS runs on fp32 operands with the 3xTF32 tensor-core path, in every compute mode: its
+    # backward dP = dS.E is a difference of nearly equal sums (sum_c softmax_c E_c - E_target, and item embeddings
+    # share a large common component after GELU), so rounding dS or E to bf16 / single-pass TF32 costs ~20 % of the
+    # gradient (measured: tools/diag_bf16.py) while the block is < 0.1 % of the step's FLOPs.
+    _CE_META = dict(x3=True)
+
     def __init__(self, args, item_num, use_modal, bert_model, pop_prob_list):
         super().__init__()
         self.args = args
@@ -41,9 +47,13 @@ class Model(torch.nn.Module):
             self.id_embedding = _IdEmbedding(item_num + 1, args.embedding_dim, padding_idx=0)
             xavier_normal_(self.id_embedding.weight.data)
         # 'auto': encode each distinct non-pad item once when that is exact (no dropout active), otherwise encode
-        # every non-pad slot.  'slots' forces the latter.  Pad slots are never encoded (their embedding is 0 and
+        # every non-pad slot.  'slots' forces the latter, 'always' the former (under dropout duplicates of an item then
+        # share one dropout mask instead of drawing independent ones -- the north star's "unique items" semantics).  Pad slots are never encoded (their embedding is 0 and
         # provably receives a zero gradient: SURVEY.md §3.2).
         self.item_dedup = "auto"
+        # multi-GPU semantics (idvs/morec_b200/parallel.py): "local" = reference-exact DDP (rank-local negatives),
+        # "global" = the G ranks act as one process with batch G*B (items encoded once, one all-gather of embeddings)
+        self.parallel_mode = getattr(args, "parallel_mode", "local")
         self.compute_dtype = getattr(args, "compute_dtype", "fp32")
         self.set_compute_dtype(self.compute_dtype)
 
@@ -63,18 +73,22 @@ class Model(torch.nn.Module):
         te = self.bert_encoder
         cfg = te.text_encoders['title'].bert_model.config
         dropout_on = self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
-        if self.item_dedup == "auto" and not dropout_on:
-            uniq, inv = torch.unique(ids_flat, return_inverse=True)
-            # first slot holding each distinct id
-            C = ids_flat.numel()
-            first = torch.full((uniq.numel(),), C, device=ids_flat.device, dtype=torch.long)
-            first.scatter_reduce_(0, inv, torch.arange(C, device=ids_flat.device), reduce="amin")
-            E_u = te(sample_items[first])
-            adt = E_u.dtype
-            return ops.GatherRowsFn.apply(E_u, inv.to(torch.int32).contiguous(), adt)
+        if self.item_dedup == "always" or (self.item_dedup == "auto" and not dropout_on):
+            # distinct non-pad ids -> first slot holding each (host index arithmetic on a C-element D2H copy)
+            ids_np = ids_flat.cpu().numpy()
+            nz = np.nonzero(ids_np)[0]
+            _, first, inv = np.unique(ids_np[nz], return_index=True, return_inverse=True)
+            dev = ids_flat.device
+            E_u = te(sample_items[torch.from_numpy(nz[first]).to(dev)])
+            s2u = np.full(ids_np.size, -1, dtype=np.int32)
+            s2u[nz] = inv.astype(np.int32)
+            return ops.GatherRowsFn.apply(E_u, torch.from_numpy(s2u).to(dev), E_u.dtype)
         return te(sample_items)
 
     def forward(self, sample_items_id, sample_items, log_mask, local_rank):
+        if self.parallel_mode == "global" and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            return self._forward_global(sample_items_id, sample_items, log_mask, local_rank)
         dev = sample_items_id.device
         if self._log_pop is None or self._log_pop.device != dev:
             self.pop_prob_list = self.pop_prob_list.to(dev)
@@ -97,5 +111,55 @@ class Model(torch.nn.Module):
         # in-batch debiased CE (model.py:45-67)
         lm = log_mask.to(torch.float32).contiguous()
         member, pad = lib.inbatch_mask(sample_items_id.reshape(B, L + 1).contiguous(), ids_flat.contiguous(), B, L)
-        loss, _ = ops.InbatchCEFn.apply(dict(x3=self.compute_dtype == "fp32"), prec_vec, score_embs, member, pad, log_pop_c, lm.reshape(-1), B, L, 0, None)
+        loss, _ = ops.InbatchCEFn.apply(self._CE_META, prec_vec.float(), score_embs.float(), member, pad, log_pop_c,
+                                        lm.reshape(-1), B, L, 0, None)
         return loss
+
+    # -------------------------------------------------------------------------------------------
+    def _forward_global(self, sample_items_id, sample_items, log_mask, local_rank):
+        """`global` multi-GPU mode: see idvs/morec_b200/parallel.py.  Equals the reference at batch G*B in one
+        process: every item of the global batch is encoded once, one all-gather of embeddings."""
+        import torch.distributed as dist
+        from .. import parallel as par
+        dev = sample_items_id.device
+        G, rank = dist.get_world_size(), dist.get_rank()
+        if self._log_pop is None or self._log_pop.device != dev:
+            self.pop_prob_list = self.pop_prob_list.to(dev)
+            self._log_pop = torch.log(self.pop_prob_list)
+        ids_flat = sample_items_id.reshape(-1).contiguous()
+        C = ids_flat.numel()
+        L = self.max_seq_len
+        B = log_mask.size(0)
+        D = self.args.embedding_dim
+        adt = torch.bfloat16 if self.compute_dtype == "bf16" else torch.float32
+        ids_all = par.all_gather_small(ids_flat).reshape(-1)                      # [G*C]
+        if self.use_modal:
+            items_all = par.all_gather_small(sample_items.contiguous()).reshape(G * C, -1)
+            plan = par.plan_global_batch(ids_all.cpu().numpy(), G, rank)          # host index arithmetic (one D2H)
+            n_mine = int(plan.my_first_slots.size)
+            my_items = items_all[torch.from_numpy(plan.my_first_slots).to(dev)]
+            E_mine = self.bert_encoder(my_items) if n_mine > 0 else torch.zeros(0, D, device=dev, dtype=adt)
+            pad_idx = np.full(plan.u_max, -1, dtype=np.int32)
+            pad_idx[:n_mine] = np.arange(n_mine, dtype=np.int32)
+            if n_mine > 0:
+                E_pad = ops.GatherRowsFn.apply(E_mine, torch.from_numpy(pad_idx).to(dev), adt)   # [u_max, D]
+            else:
+                E_pad = torch.zeros(plan.u_max, D, device=dev, dtype=adt)
+            E_table = par.AllGatherRowsFn.apply(E_pad, dist.group.WORLD)         # ONE all-gather; bwd = reduce-scatter
+            score_embs = ops.GatherRowsFn.apply(E_table, torch.from_numpy(plan.slot_to_row.astype(np.int32)).to(dev), adt)
+        else:
+            score_embs = self.id_embedding(ids_all)                                # every rank holds the full table
+        in_rows = (torch.arange(B, device=dev, dtype=torch.int32).view(B, 1) * (L + 1)
+                   + torch.arange(L, device=dev, dtype=torch.int32).view(1, L)).reshape(-1) + rank * C
+        X = ops.GatherRowsFn.apply(score_embs, in_rows.contiguous(), score_embs.dtype)
+        prec_vec = self.user_encoder(X.view(B, L, D), log_mask, local_rank).reshape(B * L, D)
+        lm = log_mask.to(torch.float32).contiguous()
+        n_valid = (lm != 0).sum().to(torch.float32).reshape(1)
+        dist.all_reduce(n_valid)                                                   # global valid-row count
+        member, pad = lib.inbatch_mask(sample_items_id.reshape(B, L + 1).contiguous(), ids_all.contiguous(), B, L)
+        log_pop_c = self._log_pop[ids_all].contiguous()
+        loss, _ = ops.InbatchCEFn.apply(self._CE_META, prec_vec.float(), score_embs.float(), member, pad,
+                                        log_pop_c, lm.reshape(-1), B, L, rank * C, n_valid)
+        # x G: DistributedDataParallel averages gradients over the G ranks; the objective is the SUM of the per-rank
+        # partial losses (each already divided by the global valid-row count)
+        return loss * float(G)

@@ -439,8 +439,9 @@ class InbatchCEFn(torch.autograd.Function):
     """loss = CE over valid rows of  S = P.E^T - log_pop  with the reject mask  (model/model.py:45-67).
 
     P [B*L, D] (rows of the local users), E [C, D] (all score columns), member/pad from lib.inbatch_mask.
-    Returns (loss, sum_cnt): loss is the local mean; sum_cnt = [sum of valid row losses, n_valid].
-    `n_valid_override` (device scalar) replaces the local count in the backward (global normalisation across ranks).
+    Returns (loss, sum_cnt): loss is the mean over the local valid rows; sum_cnt = [sum of valid row losses, n_valid].
+    `n_valid_override` (device scalar) replaces the local count in BOTH directions: loss = sum / override (the rank's
+    share of a batch-global mean, parallel.py `global` mode).
     """
 
     @staticmethod
@@ -453,6 +454,9 @@ class InbatchCEFn(torch.autograd.Function):
     def _fwd(ctx, P, E, member, pad, log_pop, log_mask, B, L, col_offset, n_valid_override):
         Pc, Ec = P.detach().contiguous(), E.detach().contiguous()
         loss, row_lse, row_loss, sum_cnt, _ = lib.inbatch_ce_fwd(Pc, Ec, member, pad, log_pop, log_mask, B, L, col_offset)
+        if n_valid_override is not None:
+            # global normalisation: this rank's share of the batch-global mean
+            loss = (sum_cnt[0] / n_valid_override.reshape(())).reshape(())
         ctx.save_for_backward(Pc, Ec, member, pad, log_pop, log_mask, row_lse, sum_cnt)
         ctx.dims = (B, L, col_offset)
         ctx.n_valid_override = n_valid_override
