@@ -53,6 +53,8 @@ def load():
         "morec_cast_f32_to_bf16": [P, P, L, P],
         "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
         "morec_clock_probe": [P, P],
+        "morec_bert_layer_fwd": [P, P],
+        "morec_bert_layer_bwd": [P, P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -179,6 +181,57 @@ def gemm_dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return 1
     raise MorecError(f"unsupported dtype {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------
+# small host<->device transfers of the per-step index plans: pinned staging ring (a pageable cudaMemcpyAsync
+# synchronises the stream; ~0.3 ms each, measured) and one combined device->host fetch per step
+# ------------------------------------------------------------------------------------------------
+_PIN_RING = []
+_PIN_NEXT = 0
+_PIN_SLOTS = 64
+_PIN_BYTES = 1 << 20
+
+
+def h2d(arr, device):
+    """numpy array -> device tensor through a ring of pinned staging buffers (async, no stream sync).  A slot is
+    reused 64 uploads later; every training step synchronises at least once, long before that."""
+    import numpy as np
+    global _PIN_NEXT
+    arr = np.ascontiguousarray(arr)
+    nbytes = arr.nbytes
+    if nbytes == 0:
+        return torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype, device=device)
+    if nbytes > _PIN_BYTES:
+        return torch.from_numpy(arr).pin_memory().to(device, non_blocking=True)
+    if not _PIN_RING:
+        for _ in range(_PIN_SLOTS):
+            _PIN_RING.append(torch.empty(_PIN_BYTES, dtype=torch.uint8).pin_memory())
+    slot = _PIN_RING[_PIN_NEXT]
+    _PIN_NEXT = (_PIN_NEXT + 1) % _PIN_SLOTS
+    src = torch.from_numpy(arr)
+    staged = slot[:nbytes].view(src.dtype).view(arr.shape)
+    staged.copy_(src)
+    return staged.to(device, non_blocking=True)
+
+
+_D2H_BUF = {}
+
+
+def d2h_many(tensors):
+    """several small device tensors -> numpy arrays with ONE stream synchronisation"""
+    outs = []
+    for i, t in enumerate(tensors):
+        t = t.contiguous()
+        key = (i, t.dtype, t.numel())
+        buf = _D2H_BUF.get(key)
+        if buf is None:
+            buf = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+            _D2H_BUF[key] = buf
+        buf.copy_(t.reshape(-1), non_blocking=True)
+        outs.append((buf, t.shape))
+    torch.cuda.current_stream().synchronize()
+    return [b.numpy().reshape(sh).copy() for b, sh in outs]
 
 
 # enum mirrors
@@ -419,6 +472,39 @@ def adamw_multi(table_dev, chunk_start_dev, n_tensors, n_chunks, beta1, beta2, e
     rc = load().morec_adamw_multi(_ptr(table_dev), _ptr(chunk_start_dev), n_tensors, n_chunks, beta1, beta2, eps, step,
                                   _ptr(inv_scale), _ptr(found_inf), int(check_finite), _stream())
     _check(rc, "morec_adamw_multi")
+
+
+class BertLayerFwd(ctypes.Structure):
+    _fields_ = ([(n, c_int) for n in ("n_tok", "n_seq", "H", "I", "n_heads", "max_len", "dtype", "_pad")]
+                + [(n, c_float) for n in ("eps", "p_hidden", "p_attn", "_padf")]
+                + [(n, c_uint64) for n in ("seed", "off_attn", "off_ln1", "off_ln2")]
+                + [(n, c_void_p) for n in ("cu_seqlens", "wqkv", "bqkv", "w_ao", "b_ao", "g1", "b1", "w_i", "b_i", "w_o",
+                                           "b_o", "g2", "b2", "x", "qkv", "ctx", "tmp_h", "x1", "rstd1", "pre", "act",
+                                           "x2", "rstd2")])
+
+
+class BertLayerBwd(ctypes.Structure):
+    _fields_ = ([("fwd", BertLayerFwd)]
+                + [(n, c_void_p) for n in ("dy", "dy2", "dz1", "dxq", "dz2", "dbr", "dx1b", "dctx", "dpre", "dqkv",
+                                           "dwqkv", "dbqkv", "dw_ao", "db_ao", "dg1", "db1", "dw_i", "db_i", "dw_o",
+                                           "db_o", "dg2", "db2")])
+
+
+_N_LAYER_FWD_LAUNCHES, _N_LAYER_BWD_LAUNCHES = 7, 17
+
+
+def bert_layer_fwd(args: BertLayerFwd):
+    global _LAUNCHES
+    rc = load().morec_bert_layer_fwd(ctypes.addressof(args), _stream())
+    _check(rc, "morec_bert_layer_fwd")
+    _LAUNCHES += _N_LAYER_FWD_LAUNCHES - 1
+
+
+def bert_layer_bwd(args: BertLayerBwd):
+    global _LAUNCHES
+    rc = load().morec_bert_layer_bwd(ctypes.addressof(args), _stream())
+    _check(rc, "morec_bert_layer_bwd")
+    _LAUNCHES += _N_LAYER_BWD_LAUNCHES - 1
 
 
 def clock_probe(out):

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 from torch.nn.init import xavier_normal_, constant_
 
-from .. import ops
+from .. import lib, ops
 from .modules import TransformerEncoder
 
 _call_counter = itertools.count(1)
@@ -104,8 +104,9 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         ps += [self.fc.weight, self.fc.bias]
         return ps
 
-    def forward(self, text):
-        """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0."""
+    def forward(self, text, am_host=None):
+        """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0.
+        am_host: optional host copy (numpy bool [n, T]) of the attention mask when the caller already fetched it."""
         n, two_t = text.shape
         T = two_t // 2
         cfg = self.bert_model.config
@@ -113,7 +114,7 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         D = self.fc.weight.shape[0]
         dev = text.device
         # ---- packing plan: ONE device->host round trip (the attention mask, n*T bytes), index arithmetic in numpy
-        am = (text[:, T:] != 0).cpu().numpy()                       # the step's only size-determining sync
+        am = am_host if am_host is not None else lib.d2h_many([text[:, T:] != 0])[0]   # size-determining sync
         lens = am.sum(axis=1)
         enc_rows = np.nonzero(lens > 0)[0]
         n_enc = int(enc_rows.size)
@@ -123,7 +124,7 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         src = enc_rows[r].astype(np.int64) * two_t + c              # flat index of every kept word piece in `text`
         cu_np = np.zeros(n_enc + 1, dtype=np.int32)
         np.cumsum(lens[enc_rows], out=cu_np[1:])
-        plan = torch.from_numpy(np.concatenate([src, c.astype(np.int64), cu_np.astype(np.int64)])).to(dev, non_blocking=True)
+        plan = lib.h2d(np.concatenate([src, c.astype(np.int64), cu_np.astype(np.int64)]), dev)
         n_tok = int(src.size)
         tok_ids = text.reshape(-1)[plan[:n_tok]].to(torch.int64).contiguous()
         tok_pos = plan[n_tok:2 * n_tok].to(torch.int32)
@@ -138,7 +139,7 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
             return E
         s2e = np.full(n, -1, dtype=np.int32)
         s2e[enc_rows] = np.arange(n_enc, dtype=np.int32)
-        return ops.GatherRowsFn.apply(E, torch.from_numpy(s2e).to(dev, non_blocking=True), adt)
+        return ops.GatherRowsFn.apply(E, lib.h2d(s2e, dev), adt)
 
 
 class Bert_Encoder(torch.nn.Module):                # reference: encoders.py:73-117
@@ -158,8 +159,9 @@ class Bert_Encoder(torch.nn.Module):                # reference: encoders.py:73-
         self.text_encoders = nn.ModuleDict({'title': Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
         self.newsname = [name for name in set(args.news_attributes) & {'title', 'abstract', 'body'}]
 
-    def forward(self, news):
-        vecs = [self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]))
+    def forward(self, news, am_host=None):
+        vecs = [self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]),
+                                            am_host if len(self.newsname) == 1 else None)
                 for name in self.newsname]
         if len(vecs) == 1:
             return vecs[0]

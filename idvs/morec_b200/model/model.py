@@ -74,15 +74,22 @@ class Model(torch.nn.Module):
         cfg = te.text_encoders['title'].bert_model.config
         dropout_on = self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
         if self.item_dedup == "always" or (self.item_dedup == "auto" and not dropout_on):
-            # distinct non-pad ids -> first slot holding each (host index arithmetic on a C-element D2H copy)
-            ids_np = ids_flat.cpu().numpy()
+            # distinct non-pad ids -> first slot holding each.  One device->host fetch (ids + attention masks, one
+            # stream sync) feeds both this index arithmetic and the token-packing plan of the text tower.
+            T = self.args.num_words_title
+            single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
+            if single:
+                ids_np, am_np = lib.d2h_many([ids_flat, sample_items[:, T:2 * T] != 0])
+            else:
+                ids_np, am_np = lib.d2h_many([ids_flat])[0], None
             nz = np.nonzero(ids_np)[0]
             _, first, inv = np.unique(ids_np[nz], return_index=True, return_inverse=True)
             dev = ids_flat.device
-            E_u = te(sample_items[torch.from_numpy(nz[first]).to(dev)])
+            rows = nz[first]
+            E_u = te(sample_items[lib.h2d(rows, dev)], am_np[rows] if am_np is not None else None)
             s2u = np.full(ids_np.size, -1, dtype=np.int32)
             s2u[nz] = inv.astype(np.int32)
-            return ops.GatherRowsFn.apply(E_u, torch.from_numpy(s2u).to(dev), E_u.dtype)
+            return ops.GatherRowsFn.apply(E_u, lib.h2d(s2u, dev), E_u.dtype)
         return te(sample_items)
 
     def forward(self, sample_items_id, sample_items, log_mask, local_rank):
@@ -135,18 +142,18 @@ class Model(torch.nn.Module):
         ids_all = par.all_gather_small(ids_flat).reshape(-1)                      # [G*C]
         if self.use_modal:
             items_all = par.all_gather_small(sample_items.contiguous()).reshape(G * C, -1)
-            plan = par.plan_global_batch(ids_all.cpu().numpy(), G, rank)          # host index arithmetic (one D2H)
+            plan = par.plan_global_batch(lib.d2h_many([ids_all])[0], G, rank)     # host index arithmetic (one D2H)
             n_mine = int(plan.my_first_slots.size)
-            my_items = items_all[torch.from_numpy(plan.my_first_slots).to(dev)]
+            my_items = items_all[lib.h2d(plan.my_first_slots, dev)]
             E_mine = self.bert_encoder(my_items) if n_mine > 0 else torch.zeros(0, D, device=dev, dtype=adt)
             pad_idx = np.full(plan.u_max, -1, dtype=np.int32)
             pad_idx[:n_mine] = np.arange(n_mine, dtype=np.int32)
             if n_mine > 0:
-                E_pad = ops.GatherRowsFn.apply(E_mine, torch.from_numpy(pad_idx).to(dev), adt)   # [u_max, D]
+                E_pad = ops.GatherRowsFn.apply(E_mine, lib.h2d(pad_idx, dev), adt)   # [u_max, D]
             else:
                 E_pad = torch.zeros(plan.u_max, D, device=dev, dtype=adt)
             E_table = par.AllGatherRowsFn.apply(E_pad, dist.group.WORLD)         # ONE all-gather; bwd = reduce-scatter
-            score_embs = ops.GatherRowsFn.apply(E_table, torch.from_numpy(plan.slot_to_row.astype(np.int32)).to(dev), adt)
+            score_embs = ops.GatherRowsFn.apply(E_table, lib.h2d(plan.slot_to_row.astype(np.int32), dev), adt)
         else:
             score_embs = self.id_embedding(ids_all)                                # every rank holds the full table
         in_rows = (torch.arange(B, device=dev, dtype=torch.int32).view(B, 1) * (L + 1)

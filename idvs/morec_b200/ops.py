@@ -133,6 +133,25 @@ def _dgrad_acc(dy, w, into):
 # ==================================================================================================
 # BERT text tower
 # ==================================================================================================
+def _layer_struct(meta, l, n_tok, n_seq, H, I, cu, w, small, acts, tmp_h):
+    """MorecBertLayerFwd for layer l.  w = (wqkv, w_ao, w_i, w_o) in compute dtype, small = fp32 (bqkv, b_ao, g1, b1,
+    b_i, b_o, g2, b2), acts = (x, qkv, ctx, x1, rstd1, pre, act, x2, rstd2)."""
+    drop, adt = meta["drop"], meta["adt"]
+    a = lib.BertLayerFwd()
+    a.n_tok, a.n_seq, a.H, a.I, a.n_heads, a.max_len = n_tok, n_seq, H, I, meta["n_heads"], meta["max_len"]
+    a.dtype = 1 if adt == torch.bfloat16 else (2 if meta.get("x3", True) else 0)
+    a.eps, a.p_hidden, a.p_attn = meta["eps"], drop.p_hidden, drop.p_attn
+    a.seed = drop.seed & 0xFFFFFFFFFFFFFFFF
+    a.off_attn, a.off_ln1, a.off_ln2 = drop.off(1 + 4 * l), drop.off(2 + 4 * l), drop.off(3 + 4 * l)
+    a.cu_seqlens = cu.data_ptr()
+    a.wqkv, a.w_ao, a.w_i, a.w_o = (t.data_ptr() for t in w)
+    a.bqkv, a.b_ao, a.g1, a.b1, a.b_i, a.b_o, a.g2, a.b2 = (t.data_ptr() for t in small)
+    a.x, a.qkv, a.ctx, a.x1, a.rstd1, a.pre, a.act, a.x2, a.rstd2 = (t.data_ptr() for t in acts)
+    a.tmp_h = tmp_h.data_ptr()
+    return a
+
+
+
 class BertTowerFn(torch.autograd.Function):
     """E[n_seq, D] = GELU(fc(BERT(tokens)[CLS])) over PACKED tokens (pad tokens and pad items are never computed).
 
@@ -162,25 +181,42 @@ class BertTowerFn(torch.autograd.Function):
         emb_saved = (x_pre if x_pre is not None else x, rstd0)
         del z
         layers = []
+        use_seq = not lib._GEMM_TIMING          # C++ layer sequencer; the per-kernel path is kept for the roofline leg
+        tmp_h = torch.empty(n_tok, H, device=dev, dtype=adt) if use_seq else None
         for l in range(n_layers):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
             wqkv, bqkv = _cw(meta["wqkv"][l], adt), meta["bqkv"][l]      # fused [3H, H] / [3H] (FusedParamGroup)
             w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
-            qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
-            ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
-            lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq,
-                         seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn,
-                         seed=drop.seed, offset=drop.off(1 + 4 * l))
-            ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
-            x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
-                                             seed=drop.seed, off_pre=drop.off(2 + 4 * l))
-            del ao
-            pre = torch.empty(n_tok, iw.shape[0], device=dev, dtype=adt)
-            act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
-            fo = lib.linear_fwd(act, w_o, ob.detach())
-            x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
-                                             seed=drop.seed, off_pre=drop.off(3 + 4 * l))
-            del fo
+            I = iw.shape[0]
+            if use_seq:
+                qkv = torch.empty(n_tok, 3 * H, device=dev, dtype=adt)
+                ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
+                x1 = torch.empty(n_tok, H, device=dev, dtype=adt)
+                x2 = torch.empty(n_tok, H, device=dev, dtype=adt)
+                pre = torch.empty(n_tok, I, device=dev, dtype=adt)
+                act = torch.empty(n_tok, I, device=dev, dtype=adt)
+                rstd = torch.empty(2, n_tok, device=dev, dtype=torch.float32)
+                rstd1, rstd2 = rstd[0], rstd[1]
+                small = (bqkv, aob.detach(), g1.detach(), b1.detach(), ib.detach(), ob.detach(), g2.detach(), b2.detach())
+                a = _layer_struct(meta, l, n_tok, n_seq, H, I, cu_seqlens, (wqkv, w_ao, w_i, w_o), small,
+                                  (x, qkv, ctxo, x1, rstd1, pre, act, x2, rstd2), tmp_h)
+                lib.bert_layer_fwd(a)
+            else:
+                qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
+                ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
+                lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq,
+                             seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn,
+                             seed=drop.seed, offset=drop.off(1 + 4 * l))
+                ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
+                x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
+                                                 seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+                del ao
+                pre = torch.empty(n_tok, I, device=dev, dtype=adt)
+                act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
+                fo = lib.linear_fwd(act, w_o, ob.detach())
+                x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
+                                                 seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+                del fo
             layers.append([x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o)])
             x = x2
         # ---- CLS pooling + fc + GELU
@@ -230,12 +266,45 @@ class BertTowerFn(torch.autograd.Function):
         dx = dx32 if adt == torch.float32 else dx32.to(adt)
         del dx32
         x_out = saved["x_last"]
+        dx2 = None                         # second addend of the running hidden-state gradient (sequencer path)
+        use_seq = not lib._GEMM_TIMING
+        if use_seq:
+            I = params[5 + 10].shape[0]
+            ws_h = torch.empty(4 if drop.p_hidden > 0 else 3, n_tok, H, device=dev, dtype=adt)   # dz2, dx1b, dctx, (dbr)
+            dpre_ws = torch.empty(n_tok, I, device=dev, dtype=adt)
+            dqkv_ws = torch.empty(n_tok, 3 * H, device=dev, dtype=adt)
         for l in reversed(range(n_layers)):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
             x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o) = saved["layers"][l]
             base = 5 + 16 * l
             # gradients of the three projection weights / biases are row blocks of one fused buffer
             dwqkv, dbqkv = arena.take((3 * H, H)), arena.take((3 * H,))
+            if use_seq:
+                dg2, db2, dob, dow, dib, diw = _z(g2), _z(b2), _z(ob), _z(ow), _z(ib), _z(iw)
+                dg1, db1, daob, daow = _z(g1), _z(b1), _z(aob), _z(aow)
+                small = (meta["bqkv"][l], aob.detach(), g1.detach(), b1.detach(), ib.detach(), ob.detach(), g2.detach(),
+                         b2.detach())
+                b = lib.BertLayerBwd()
+                b.fwd = _layer_struct(meta, l, n_tok, n_seq, H, iw.shape[0], cu_seqlens, (wqkv, w_ao, w_i, w_o), small,
+                                      (x, qkv, ctxo, x1, rstd1, pre, act, x_out, rstd2), ws_h[0])
+                dz1 = torch.empty(n_tok, H, device=dev, dtype=adt)
+                dxq = torch.empty(n_tok, H, device=dev, dtype=adt)
+                b.dy, b.dy2 = dx.data_ptr(), (dx2.data_ptr() if dx2 is not None else None)
+                b.dz1, b.dxq = dz1.data_ptr(), dxq.data_ptr()
+                b.dz2, b.dx1b, b.dctx = ws_h[0].data_ptr(), ws_h[1].data_ptr(), ws_h[2].data_ptr()
+                b.dbr = ws_h[3].data_ptr() if drop.p_hidden > 0 else None
+                b.dpre, b.dqkv = dpre_ws.data_ptr(), dqkv_ws.data_ptr()
+                (b.dwqkv, b.dbqkv, b.dw_ao, b.db_ao, b.dg1, b.db1, b.dw_i, b.db_i, b.dw_o, b.db_o, b.dg2, b.db2) = (
+                    t.data_ptr() for t in (dwqkv, dbqkv, daow, daob, dg1, db1, diw, dib, dow, dob, dg2, db2))
+                lib.bert_layer_bwd(b)
+                dx, dx2 = dz1, dxq
+                x_out = x
+                lay = (dwqkv[:H], dbqkv[:H], dwqkv[H:2 * H], dbqkv[H:2 * H], dwqkv[2 * H:], dbqkv[2 * H:],
+                       daow, daob, dg1, db1, diw, dib, dow, dob, dg2, db2)
+                for j, g in enumerate(lay):
+                    grads[base + j] = g if need[base + j] else None
+                saved["layers"][l] = None
+                continue
             # output LayerNorm (y = x_out)
             dg2, db2, dob = _z(g2), _z(b2), _z(ob)
             dz2, dfo = lib.layernorm_bwd(dx, x_out, g2.detach(), b2.detach(), rstd2, dgamma=dg2, dbeta=db2, dbias=dob,
@@ -283,8 +352,8 @@ class BertTowerFn(torch.autograd.Function):
         y_emb, rstd0 = saved["emb"]
         deg, deb = _z(eg), _z(eb)
         dtype_sum = arena.take((H,))
-        dz0, _ = lib.layernorm_bwd(dx, y_emb, eg.detach(), eb.detach(), rstd0, dgamma=deg, dbeta=deb, dbias=dtype_sum,
-                                   p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
+        dz0, _ = lib.layernorm_bwd(dx, y_emb, eg.detach(), eb.detach(), rstd0, dy2=dx2, dgamma=deg, dbeta=deb,
+                                   dbias=dtype_sum, p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
         dword = _z(word) if need[0] else None
         dposw = _z(posw) if need[1] else None
         if dword is not None or dposw is not None:

@@ -166,6 +166,40 @@ int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_ten
  * bench.py report the SM clock under load without NVML queries inside the timed region (they stall launches). */
 int morec_clock_probe(uint64_t* out_cycles_ns, void* stream);
 
+/* ---- one BERT encoder layer per call (host-side sequencing in C++: 7 launches forward, 17 backward) -----------
+ * Replaces HF BertLayer.forward and its autograd backward (call site model/encoders.py:68) for PACKED tokens.
+ * All pointers are caller-allocated device buffers.  Weight matrices are in the compute dtype (fp32 for dtype 0/2,
+ * bf16 shadows for dtype 1); biases / LayerNorm parameters / rstd and all parameter gradients are fp32.
+ *   forward : x -> qkv[n_tok,3H] -> ctx[n_tok,H] -> x1 = LN(x + drop(ctx Wo^T + bo)) -> pre/act[n_tok,I] ->
+ *             x2 = LN(x1 + drop(act Wo2^T + bo2));   tmp_h[n_tok,H] is scratch.
+ *   backward: (dy + dy2) = grad of x2  ->  grad of x returned as TWO addends dz1 and dxq (the layer below feeds them
+ *             to its own output LayerNorm backward as dy / dy2, so the sum is never materialised).
+ *             Parameter gradients are ACCUMULATED into zero-initialised fp32 buffers (split-K TMA reduce-add).
+ *             scratch: dz2, dbr, dx1b, dctx [n_tok,H]; dpre [n_tok,I]; dqkv [n_tok,3H].
+ */
+typedef struct MorecBertLayerFwd {
+    int n_tok, n_seq, H, I, n_heads, max_len, dtype, _pad;
+    float eps, p_hidden, p_attn, _padf;
+    uint64_t seed, off_attn, off_ln1, off_ln2;
+    const int32_t* cu_seqlens;
+    const void* wqkv; const float* bqkv;
+    const void* w_ao; const float* b_ao; const float* g1; const float* b1;
+    const void* w_i; const float* b_i;
+    const void* w_o; const float* b_o; const float* g2; const float* b2;
+    const void* x; void* qkv; void* ctx; void* tmp_h; void* x1; float* rstd1; void* pre; void* act; void* x2; float* rstd2;
+} MorecBertLayerFwd;
+int morec_bert_layer_fwd(const MorecBertLayerFwd* args, void* stream);
+
+typedef struct MorecBertLayerBwd {
+    MorecBertLayerFwd fwd;            /* the forward's parameters and saved activations */
+    const void* dy; const void* dy2;  /* gradient of x2 (dy2 may be null) */
+    void* dz1; void* dxq;             /* outputs: the two addends of the gradient of x */
+    void* dz2; void* dbr; void* dx1b; void* dctx; void* dpre; void* dqkv;   /* scratch */
+    float* dwqkv; float* dbqkv; float* dw_ao; float* db_ao; float* dg1; float* db1;
+    float* dw_i; float* db_i; float* dw_o; float* db_o; float* dg2; float* db2;
+} MorecBertLayerBwd;
+int morec_bert_layer_bwd(const MorecBertLayerBwd* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
