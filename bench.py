@@ -287,13 +287,19 @@ def main():
     sync()
     if mon:
         mon.edge()
+    ms0 = torch.cuda.memory_stats(dev)
     t_wall0 = time.time()
+    step_t = []
     e0.record()
     for i in range(K):
         step(*resident[W + i])
         if mon:
             mon.probe()
+        step_t.append(time.time())
     e1.record()
+    ms1 = torch.cuda.memory_stats(dev)
+    alloc_delta = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
+    step_host_ms = [round(1e3 * (b - a), 1) for a, b in zip([t_wall0] + step_t[:-1], step_t)]
     t_issue = time.time() - t_wall0          # host time to enqueue K steps (includes the in-step size syncs)
     sync()
     if mon:
@@ -371,7 +377,8 @@ def main():
                        "dropout": cfg["drop"], "optimizer": "FusedAdamW (2 groups)",
                        "items_encoded": "each distinct non-pad item of the (global) batch once; pad tokens skipped"},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+            "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "host_ms_each_step": step_host_ms,
+            "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -133,43 +133,55 @@ __device__ __forceinline__ float mask_add(const AttnParams& p, int s, int i, int
     return ok ? 0.f : p.masked_add;
 }
 
-// scores + softmax for lane i: on return pr[j] = softmax_j (un-dropped probabilities), j < len
+// ---------------------------------------------------------------------------------------------------------------
+// Score rows live in shared memory (Srow[lane*33 + j], conflict-free) rather than in registers: the loops over keys
+// then stay rolled (a fully unrolled 32-key x 64-dim body overflowed the instruction cache: ncu showed 41 % of the
+// stall samples as "no_instructions").
+// ---------------------------------------------------------------------------------------------------------------
+
+// S[lane][j] = <q_lane, k_j> over the whole head dim (raw, unscaled); rows j >= len hold garbage that is never read
 template <typename T>
-__device__ __forceinline__ void scores_softmax(const AttnParams& p, float* tile, int s, int h, int row0, int len,
-                                               int lane, float (&pr)[AT_MAXL]) {
-    const T* Q = reinterpret_cast<const T*>(p.q);
-    const T* K = reinterpret_cast<const T*>(p.k);
-#pragma unroll
-    for (int j = 0; j < AT_MAXL; ++j) pr[j] = 0.f;
+__device__ __forceinline__ void raw_scores(const AttnParams& p, float* tile, float* S, const T* Qb, int ldq, const T* Kb,
+                                           int h, int row0, int len, int lane) {
+    const int len4 = (len + 3) & ~3;
     for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
         const int w = min(AT_DCH, p.head_dim - dc);
         __syncwarp();
-        load_tile<T>(tile, K, p.ld, row0, len, h * p.head_dim + dc, w, lane);
+        load_tile<T>(tile, Kb, p.ld, row0, len, h * p.head_dim + dc, w, lane);
         __syncwarp();
         float qv[AT_DCH];
-        load_row<T>(qv, Q + (size_t)(row0 + (lane < len ? lane : 0)) * p.ld + h * p.head_dim + dc, w, lane < len);
-        // rows >= len of the tile hold stale data: their scores are discarded below (pr[j >= len] := 0)
-#pragma unroll
-        for (int j0 = 0; j0 < AT_MAXL; j0 += 4) {
-            if (j0 < len) dot4keys(qv, tile, j0, w, pr[j0], pr[j0 + 1], pr[j0 + 2], pr[j0 + 3]);
+        load_row<T>(qv, Qb + (size_t)(row0 + (lane < len ? lane : 0)) * ldq + h * p.head_dim + dc, w, lane < len);
+#pragma unroll 1
+        for (int j0 = 0; j0 < len4; j0 += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            dot4keys(qv, tile, j0, w, a0, a1, a2, a3);
+            float* sr = S + lane * 33 + j0;
+            if (dc == 0) { sr[0] = a0; sr[1] = a1; sr[2] = a2; sr[3] = a3; }
+            else { sr[0] += a0; sr[1] += a1; sr[2] += a2; sr[3] += a3; }
         }
     }
+}
+
+// in-place softmax of row `lane` of S over j < len (scale + additive mask first)
+__device__ __forceinline__ void softmax_row(const AttnParams& p, float* S, int s, int len, int lane) {
+    float* sr = S + lane * 33;
     float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < AT_MAXL; ++j) {
-        if (j < len) {
-            pr[j] = pr[j] * p.scale + mask_add(p, s, lane, j);
-            m = fmaxf(m, pr[j]);
-        }
+#pragma unroll 1
+    for (int j = 0; j < len; ++j) {
+        const float x = sr[j] * p.scale + mask_add(p, s, lane, j);
+        sr[j] = x;
+        m = fmaxf(m, x);
     }
     float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < AT_MAXL; ++j) {
-        if (j < len) { pr[j] = __expf(pr[j] - m); sum += pr[j]; }
+#pragma unroll 1
+    for (int j = 0; j < len; ++j) {
+        const float e = __expf(sr[j] - m);
+        sr[j] = e;
+        sum += e;
     }
     const float inv = 1.f / sum;
-#pragma unroll
-    for (int j = 0; j < AT_MAXL; ++j) pr[j] = j < len ? pr[j] * inv : 0.f;
+#pragma unroll 1
+    for (int j = 0; j < len; ++j) sr[j] *= inv;
 }
 
 // dropout keep mask bits for row (pair, i): bit j set = keep
@@ -177,7 +189,7 @@ __device__ __forceinline__ uint32_t keep_bits(const AttnParams& p, int pair, int
     if (!(p.dropout_p > 0.f)) return 0xffffffffu;
     const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
     uint32_t bits = 0;
-#pragma unroll
+#pragma unroll 1
     for (int g = 0; g < AT_MAXL / 4; ++g) {
         if (4 * g < len) {
             const uint4 r = Philox::gen(p.seed, p.offset + ((uint64_t)pair * AT_MAXL + i) * (AT_MAXL / 4) + g);
@@ -190,62 +202,72 @@ __device__ __forceinline__ uint32_t keep_bits(const AttnParams& p, int pair, int
     return bits;
 }
 
+// out_lane[0..w) = sum_j coef(lane, j) * tile[j][0..w)      coef read from a [32][33] smem matrix, row- or column-wise
+template <bool TRANSPOSED>
+__device__ __forceinline__ void weighted_rows(const float* coef, const float* tile, int len, int lane,
+                                              float (&acc)[AT_DCH]) {
+#pragma unroll
+    for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+        const float d = TRANSPOSED ? coef[j * 33 + lane] : coef[lane * 33 + j];
+        const float4* r = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+#pragma unroll
+        for (int t = 0; t < AT_DCH / 4; ++t) {
+            const float4 x = r[t];
+            acc[4 * t] += d * x.x; acc[4 * t + 1] += d * x.y; acc[4 * t + 2] += d * x.z; acc[4 * t + 3] += d * x.w;
+        }
+    }
+}
+
+constexpr int AT_FWD_SMEM_FLOATS = AT_WARPS * (AT_MAXL * AT_DCH + AT_MAXL * 33);
+
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_kernel(const AttnParams p) {
-    __shared__ __align__(16) float tiles[AT_WARPS][AT_MAXL * AT_DCH];
+    extern __shared__ __align__(16) float at_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = tiles[warp];
+    float* tile = at_smem + warp * (AT_MAXL * AT_DCH);
+    float* S = at_smem + AT_WARPS * (AT_MAXL * AT_DCH) + warp * (AT_MAXL * 33);
     const int n_pairs = p.n_seq * p.n_heads;
+    const T* Q = reinterpret_cast<const T*>(p.q);
+    const T* K = reinterpret_cast<const T*>(p.k);
+    const T* V = reinterpret_cast<const T*>(p.v);
+    T* O = reinterpret_cast<T*>(p.out);
     for (int pair = blockIdx.x * AT_WARPS + warp; pair < n_pairs; pair += gridDim.x * AT_WARPS) {
         const int s = pair / p.n_heads, h = pair - s * p.n_heads;
         int row0, len;
         seq_range(p, s, row0, len);
         if (len <= 0) continue;
-        float pr[AT_MAXL];
-        scores_softmax<T>(p, tile, s, h, row0, len, lane, pr);
+        raw_scores<T>(p, tile, S, Q, p.ld, K, h, row0, len, lane);
+        softmax_row(p, S, s, len, lane);
         if (p.dropout_p > 0.f) {
             const uint32_t kb = keep_bits(p, pair, lane, len);
             const float sc = 1.f / (1.f - p.dropout_p);
-#pragma unroll
-            for (int j = 0; j < AT_MAXL; ++j) pr[j] = ((kb >> j) & 1u) ? pr[j] * sc : 0.f;
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) S[lane * 33 + j] = ((kb >> j) & 1u) ? S[lane * 33 + j] * sc : 0.f;
         }
-        const T* V = reinterpret_cast<const T*>(p.v);
-        T* O = reinterpret_cast<T*>(p.out);
         for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
             const int w = min(AT_DCH, p.head_dim - dc);
             __syncwarp();
             load_tile<T>(tile, V, p.ld, row0, len, h * p.head_dim + dc, w, lane);
             __syncwarp();
             float ov[AT_DCH];
-#pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) ov[t] = 0.f;
-#pragma unroll
-            for (int j = 0; j < AT_MAXL; ++j) {
-                if (j < len) {
-                    const float4* vr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
-                    const float pj = pr[j];
-#pragma unroll
-                    for (int t = 0; t < AT_DCH / 4; ++t) {
-                        const float4 vv = vr[t];
-                        ov[4 * t] += pj * vv.x; ov[4 * t + 1] += pj * vv.y; ov[4 * t + 2] += pj * vv.z; ov[4 * t + 3] += pj * vv.w;
-                    }
-                }
-            }
-            if (lane < len) {
-                T* orow = O + (size_t)(row0 + lane) * p.ld_o + h * p.head_dim + dc;
-store_row<T>(orow, ov, w);
-            }
+            weighted_rows<false>(S, tile, len, lane, ov);
+            if (lane < len) store_row<T>(O + (size_t)(row0 + lane) * p.ld_o + h * p.head_dim + dc, ov, w);
         }
+        __syncwarp();
     }
 }
+
+constexpr int AT_BWD_SMEM_FLOATS = AT_WARPS * (AT_MAXL * AT_DCH + 2 * AT_MAXL * 33);
 
 template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParams p) {
     extern __shared__ __align__(16) float at_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tile = at_smem + warp * (AT_MAXL * AT_DCH);                                   // [32][64] stream tile
-    float* Pw = at_smem + AT_WARPS * (AT_MAXL * AT_DCH) + warp * (2 * AT_MAXL * 33);      // P~[i][j] (dropped, rescaled)
-    float* dSw = Pw + AT_MAXL * 33;                                                      // dS[i][j] * scale
+    float* Pw = at_smem + AT_WARPS * (AT_MAXL * AT_DCH) + warp * (2 * AT_MAXL * 33);      // P, then P~ (dropped, rescaled)
+    float* dSw = Pw + AT_MAXL * 33;                                                      // dP~, then dS * scale
     const int n_pairs = p.n_seq * p.n_heads;
     const T* Q = reinterpret_cast<const T*>(p.q);
     const T* K = reinterpret_cast<const T*>(p.k);
@@ -260,112 +282,66 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
         seq_range(p, s, row0, len);
         if (len <= 0) continue;
         const int col_h = h * p.head_dim;
-        float pr[AT_MAXL];
-        scores_softmax<T>(p, tile, s, h, row0, len, lane, pr);
-        // ---- dP~[i][j] = dO_i . V_j
-        float dp[AT_MAXL];
-#pragma unroll
-        for (int j = 0; j < AT_MAXL; ++j) dp[j] = 0.f;
-        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
-            const int w = min(AT_DCH, p.head_dim - dc);
-            __syncwarp();
-            load_tile<T>(tile, V, p.ld, row0, len, col_h + dc, w, lane);
-            __syncwarp();
-            float gv[AT_DCH];
-            load_row<T>(gv, dO + (size_t)(row0 + (lane < len ? lane : 0)) * p.ld_o + col_h + dc, w, lane < len);
-#pragma unroll
-            for (int j0 = 0; j0 < AT_MAXL; j0 += 4) {
-                if (j0 < len) dot4keys(gv, tile, j0, w, dp[j0], dp[j0 + 1], dp[j0 + 2], dp[j0 + 3]);
-            }
+        // P = softmax(QK^T) ; dP~[i][j] = dO_i . V_j   (same inner product routine: "queries" = dO rows, "keys" = V)
+        raw_scores<T>(p, tile, Pw, Q, p.ld, K, h, row0, len, lane);
+        softmax_row(p, Pw, s, len, lane);
+        {
+            AttnParams pv = p;           // reuse raw_scores with V as the key matrix
+            raw_scores<T>(pv, tile, dSw, dO, p.ld_o, V, h, row0, len, lane);
         }
-        // ---- softmax backward (with dropout on P): dS = P * (dP - sum_k P_k dP_k), dP = keep * dP~ / (1-p)
+        // softmax backward (dropout on P): dP = keep * dP~ / (1-p);  dS = P * (dP - sum_k P_k dP_k) * scale
         {
             const uint32_t kb = keep_bits(p, pair, lane, len);
             const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+            float* pr = Pw + lane * 33;
+            float* dr = dSw + lane * 33;
             float dsum = 0.f;
-#pragma unroll
-            for (int j = 0; j < AT_MAXL; ++j) {
+            const bool act = lane < len;
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) {
                 const float keep = ((kb >> j) & 1u) ? sc : 0.f;
-                dp[j] = j < len ? dp[j] * keep : 0.f;   // dP w.r.t. un-dropped probabilities (stale keys -> 0)
-                dsum += pr[j] * dp[j];
-                Pw[lane * 33 + j] = pr[j] * keep;   // P~ for dV
+                const float d = act ? dr[j] * keep : 0.f;
+                dr[j] = d;
+                dsum += (act ? pr[j] : 0.f) * d;
             }
-#pragma unroll
-            for (int j = 0; j < AT_MAXL; ++j) dSw[lane * 33 + j] = (lane < len && j < len) ? pr[j] * (dp[j] - dsum) * p.scale : 0.f;
-            if (lane >= len) {
-#pragma unroll
-                for (int j = 0; j < AT_MAXL; ++j) Pw[lane * 33 + j] = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) {
+                const float keep = ((kb >> j) & 1u) ? sc : 0.f;
+                const float pj = act ? pr[j] : 0.f;
+                dr[j] = pj * (dr[j] - dsum) * p.scale;     // dS (scaled)
+                pr[j] = pj * keep;                           // P~ for dV
             }
         }
         __syncwarp();
-        // ---- dQ_i = sum_j dS_ij K_j        (lane = query i; K chunk broadcast from smem)
+        // dQ_i = sum_j dS_ij K_j        (lane = query i; K chunk broadcast from smem)
         for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
             const int w = min(AT_DCH, p.head_dim - dc);
             __syncwarp();
             load_tile<T>(tile, K, p.ld, row0, len, col_h + dc, w, lane);
             __syncwarp();
             float acc[AT_DCH];
-#pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
-            for (int j = 0; j < len; ++j) {
-                const float d = dSw[lane * 33 + j];
-                const float4* kr = reinterpret_cast<const float4*>(tile + j * AT_DCH);
-#pragma unroll
-                for (int t = 0; t < AT_DCH / 4; ++t) {
-                    const float4 kk = kr[t];
-                    acc[4 * t] += d * kk.x; acc[4 * t + 1] += d * kk.y; acc[4 * t + 2] += d * kk.z; acc[4 * t + 3] += d * kk.w;
-                }
-            }
-            if (lane < len) {
-                T* r = dQ + (size_t)(row0 + lane) * p.ld + col_h + dc;
-store_row<T>(r, acc, w);
-            }
+            weighted_rows<false>(dSw, tile, len, lane, acc);
+            if (lane < len) store_row<T>(dQ + (size_t)(row0 + lane) * p.ld + col_h + dc, acc, w);
         }
-        // ---- dK_j = sum_i dS_ij Q_i        (lane = key j; Q chunk broadcast from smem)
+        // dK_j = sum_i dS_ij Q_i        (lane = key j; Q chunk broadcast from smem)
         for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
             const int w = min(AT_DCH, p.head_dim - dc);
             __syncwarp();
             load_tile<T>(tile, Q, p.ld, row0, len, col_h + dc, w, lane);
             __syncwarp();
             float acc[AT_DCH];
-#pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
-            for (int i = 0; i < len; ++i) {
-                const float d = dSw[i * 33 + lane];
-                const float4* qr = reinterpret_cast<const float4*>(tile + i * AT_DCH);
-#pragma unroll
-                for (int t = 0; t < AT_DCH / 4; ++t) {
-                    const float4 qq = qr[t];
-                    acc[4 * t] += d * qq.x; acc[4 * t + 1] += d * qq.y; acc[4 * t + 2] += d * qq.z; acc[4 * t + 3] += d * qq.w;
-                }
-            }
-            if (lane < len) {
-                T* r = dK + (size_t)(row0 + lane) * p.ld + col_h + dc;
-store_row<T>(r, acc, w);
-            }
+            weighted_rows<true>(dSw, tile, len, lane, acc);
+            if (lane < len) store_row<T>(dK + (size_t)(row0 + lane) * p.ld + col_h + dc, acc, w);
         }
-        // ---- dV_j = sum_i P~_ij dO_i       (lane = key j; dO chunk broadcast from smem)
+        // dV_j = sum_i P~_ij dO_i       (lane = key j; dO chunk broadcast from smem)
         for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
             const int w = min(AT_DCH, p.head_dim - dc);
             __syncwarp();
             load_tile<T>(tile, dO, p.ld_o, row0, len, col_h + dc, w, lane);
             __syncwarp();
             float acc[AT_DCH];
-#pragma unroll
-            for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
-            for (int i = 0; i < len; ++i) {
-                const float d = Pw[i * 33 + lane];
-                const float4* gr = reinterpret_cast<const float4*>(tile + i * AT_DCH);
-#pragma unroll
-                for (int t = 0; t < AT_DCH / 4; ++t) {
-                    const float4 gg = gr[t];
-                    acc[4 * t] += d * gg.x; acc[4 * t + 1] += d * gg.y; acc[4 * t + 2] += d * gg.z; acc[4 * t + 3] += d * gg.w;
-                }
-            }
-            if (lane < len) {
-                T* r = dV + (size_t)(row0 + lane) * p.ld + col_h + dc;
-store_row<T>(r, acc, w);
-            }
+            weighted_rows<true>(Pw, tile, len, lane, acc);
+            if (lane < len) store_row<T>(dV + (size_t)(row0 + lane) * p.ld + col_h + dc, acc, w);
         }
         __syncwarp();
     }
@@ -399,8 +375,15 @@ extern "C" int morec_attn_fwd(const void* q, const void* k, const void* v, void*
     int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
     const int cap = num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    if (dtype == 0) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-    else attn_fwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    constexpr size_t smem = (size_t)AT_FWD_SMEM_FLOATS * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    if (dtype == 0) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    else attn_fwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -421,7 +404,7 @@ extern "C" int morec_attn_bwd(const void* q, const void* k, const void* v, const
     int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
     const int cap = num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    constexpr size_t smem = (size_t)AT_WARPS * (AT_MAXL * AT_DCH + 2 * AT_MAXL * 33) * sizeof(float);
+    constexpr size_t smem = (size_t)AT_BWD_SMEM_FLOATS * sizeof(float);
     static bool attr = false;
     if (!attr) {
         MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

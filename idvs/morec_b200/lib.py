@@ -303,11 +303,14 @@ def _u64(x):
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, residual=None, pos=None, pos_period=0, p_pre=0.0, p_post=0.0, seed=0,
-                  off_pre=0, off_post=0, out=None):
+                  off_pre=0, off_post=0, out=None, y_pre=None):
     """returns (y, y_pre_or_None, rstd)"""
     M, H = x.shape
     y = out if out is not None else torch.empty_like(x)
-    y_pre = torch.empty_like(x) if p_post > 0 else None
+    if p_post > 0 and y_pre is None:
+        y_pre = torch.empty_like(x)
+    if not (p_post > 0):
+        y_pre = None
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
     rc = load().morec_layernorm_fwd(_ptr(x), _ptr(residual), _ptr(pos), pos_period, _ptr(gamma), _ptr(beta),
                                     _ptr(y), _ptr(y_pre), _ptr(rstd), M, H, eps,

@@ -84,6 +84,52 @@ class _Arena:
         return v
 
 
+class _Workspace:
+    """Grow-only device buffer with a bump allocator for the token-count-dependent activations of the text tower.
+
+    Batches differ in packed token count, so every step would otherwise ask the caching allocator for a new set of
+    block sizes (observed: cudaMalloc / cuMemMap stalls of tens of ms whenever unseen sizes arrive).  The workspace
+    reaches its steady-state size on the largest batch and is then reused verbatim.  A workspace is owned by one
+    forward pass until its backward has run; a second concurrent owner falls back to ordinary torch.empty."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.busy = False
+
+    def acquire(self, dev, nbytes):
+        if self.busy:
+            return False
+        if self.buf is None or self.buf.device != dev or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes * 1.1) + (1 << 20), device=dev, dtype=torch.uint8)
+        self.off = 0
+        self.busy = True
+        return True
+
+    def release(self):
+        self.busy = False
+
+    def take(self, shape, dtype):
+        n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+        start = (self.off + 255) // 256 * 256
+        if self.buf is None or start + n > self.buf.numel():
+            return torch.empty(shape, device=self.buf.device if self.buf is not None else None, dtype=dtype)
+        self.off = start + n
+        return self.buf[start:start + n].view(dtype).view(shape)
+
+
+_WS_FWD = {}
+_WS_BWD = {}
+
+
+def _ws(table, dev):
+    key = (dev.type, dev.index)
+    if key not in table:
+        table[key] = _Workspace()
+    return table[key]
+
+
 class FusedParamGroup:
     """Keeps several nn.Parameters (e.g. the Q, K, V projection weights) as consecutive row blocks of ONE contiguous
     buffer by re-pointing their .data, so the fused [3H, H] projection weight exists without a per-step concat.
@@ -173,29 +219,33 @@ class BertTowerFn(torch.autograd.Function):
         dh = H // n_heads
         dev = word.device
         scale = 1.0 / math.sqrt(dh)
+        es = 2 if adt == torch.bfloat16 else 4
+        I0 = params[5 + 10].shape[0]
+        ws = _ws(_WS_FWD, dev)
+        own_ws = ws.acquire(dev, n_tok * es * (n_layers * (6 * H + 2 * I0) + 6 * H) + n_layers * n_tok * 8
+                            + (n_layers * 8 + 16) * 256)
+        new = (lambda shape, dtype=adt: ws.take(shape, dtype)) if own_ws else \
+              (lambda shape, dtype=adt: torch.empty(shape, device=dev, dtype=dtype))
         # ---- embeddings: gather + LN (+ dropout after LN: HF BertEmbeddings)
-        z = torch.empty(n_tok, H, device=dev, dtype=adt)
+        z = new((n_tok, H))
         lib.bert_embed_fwd(tok_ids, tok_pos, word.detach(), posw.detach(), typew.detach()[0].contiguous(), z)
         x, x_pre, rstd0 = lib.layernorm_fwd(z, eg.detach(), eb.detach(), eps, p_post=drop.p_hidden, seed=drop.seed,
-                                            off_post=drop.off(0))
+                                            off_post=drop.off(0), out=new((n_tok, H)),
+                                            y_pre=new((n_tok, H)) if drop.p_hidden > 0 else None)
         emb_saved = (x_pre if x_pre is not None else x, rstd0)
         del z
         layers = []
         use_seq = not lib._GEMM_TIMING          # C++ layer sequencer; the per-kernel path is kept for the roofline leg
-        tmp_h = torch.empty(n_tok, H, device=dev, dtype=adt) if use_seq else None
+        tmp_h = new((n_tok, H)) if use_seq else None
         for l in range(n_layers):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
             wqkv, bqkv = _cw(meta["wqkv"][l], adt), meta["bqkv"][l]      # fused [3H, H] / [3H] (FusedParamGroup)
             w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
             I = iw.shape[0]
             if use_seq:
-                qkv = torch.empty(n_tok, 3 * H, device=dev, dtype=adt)
-                ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
-                x1 = torch.empty(n_tok, H, device=dev, dtype=adt)
-                x2 = torch.empty(n_tok, H, device=dev, dtype=adt)
-                pre = torch.empty(n_tok, I, device=dev, dtype=adt)
-                act = torch.empty(n_tok, I, device=dev, dtype=adt)
-                rstd = torch.empty(2, n_tok, device=dev, dtype=torch.float32)
+                qkv, ctxo, x1, x2 = new((n_tok, 3 * H)), new((n_tok, H)), new((n_tok, H)), new((n_tok, H))
+                pre, act = new((n_tok, I)), new((n_tok, I))
+                rstd = new((2, n_tok), torch.float32)
                 rstd1, rstd2 = rstd[0], rstd[1]
                 small = (bqkv, aob.detach(), g1.detach(), b1.detach(), ib.detach(), ob.detach(), g2.detach(), b2.detach())
                 a = _layer_struct(meta, l, n_tok, n_seq, H, I, cu_seqlens, (wqkv, w_ao, w_i, w_o), small,
@@ -226,6 +276,10 @@ class BertTowerFn(torch.autograd.Function):
         w_fc = _cw(fc_w, adt)
         E = lib.linear_fwd(cls, w_fc, fc_b.detach(), epilogue=lib.EPI_GELU, pre=fc_pre)
         ctx.meta = meta
+        ctx.own_ws = own_ws
+        if own_ws and not torch.is_grad_enabled():
+            ws.release()                      # no backward will come (eval / no_grad): nothing stays saved
+            ctx.own_ws = False
         ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre, w_fc=w_fc)
         ctx.idx = (tok_ids, tok_pos, cu_seqlens, cls_rows)
         ctx.params = params
@@ -268,11 +322,17 @@ class BertTowerFn(torch.autograd.Function):
         x_out = saved["x_last"]
         dx2 = None                         # second addend of the running hidden-state gradient (sequencer path)
         use_seq = not lib._GEMM_TIMING
+        wsb = _ws(_WS_BWD, dev)
+        es = 2 if adt == torch.bfloat16 else 4
+        I = params[5 + 10].shape[0]
+        own_b = use_seq and wsb.acquire(dev, n_tok * es * (12 * H + I) + 64 * 256)
+        newb = (lambda shape, dtype=adt: wsb.take(shape, dtype)) if own_b else \
+               (lambda shape, dtype=adt: torch.empty(shape, device=dev, dtype=dtype))
         if use_seq:
-            I = params[5 + 10].shape[0]
-            ws_h = torch.empty(4 if drop.p_hidden > 0 else 3, n_tok, H, device=dev, dtype=adt)   # dz2, dx1b, dctx, (dbr)
-            dpre_ws = torch.empty(n_tok, I, device=dev, dtype=adt)
-            dqkv_ws = torch.empty(n_tok, 3 * H, device=dev, dtype=adt)
+            ws_h = newb((4 if drop.p_hidden > 0 else 3, n_tok, H))   # dz2, dx1b, dctx, (dbr)
+            dpre_ws = newb((n_tok, I))
+            dqkv_ws = newb((n_tok, 3 * H))
+            pp = [newb((n_tok, H)) for _ in range(4)]                # ping-pong pairs for (dz1, dxq)
         for l in reversed(range(n_layers)):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
             x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o) = saved["layers"][l]
@@ -287,8 +347,7 @@ class BertTowerFn(torch.autograd.Function):
                 b = lib.BertLayerBwd()
                 b.fwd = _layer_struct(meta, l, n_tok, n_seq, H, iw.shape[0], cu_seqlens, (wqkv, w_ao, w_i, w_o), small,
                                       (x, qkv, ctxo, x1, rstd1, pre, act, x_out, rstd2), ws_h[0])
-                dz1 = torch.empty(n_tok, H, device=dev, dtype=adt)
-                dxq = torch.empty(n_tok, H, device=dev, dtype=adt)
+                dz1, dxq = pp[2 * (l & 1)], pp[2 * (l & 1) + 1]
                 b.dy, b.dy2 = dx.data_ptr(), (dx2.data_ptr() if dx2 is not None else None)
                 b.dz1, b.dxq = dz1.data_ptr(), dxq.data_ptr()
                 b.dz2, b.dx1b, b.dctx = ws_h[0].data_ptr(), ws_h[1].data_ptr(), ws_h[2].data_ptr()
@@ -366,6 +425,11 @@ class BertTowerFn(torch.autograd.Function):
         grads[3] = deg if need[3] else None
         grads[4] = deb if need[4] else None
         ctx.saved = None
+        if own_b:
+            wsb.release()
+        if getattr(ctx, "own_ws", False):
+            _ws(_WS_FWD, dev).release()
+            ctx.own_ws = False
         return (None, None, None, None, None) + tuple(grads)
 
 
