@@ -42,7 +42,8 @@ constexpr int BLOCK_M = 128;
 constexpr int kThreads = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-7 epilogue
 constexpr int kEpiWarps = 4;
 constexpr int kEpiBufBytes = 4096;   // one 32-row x 128B sub-tile (32 fp32 or 64 bf16 columns), SWIZZLE_128B
-constexpr int kEpiBufsPerWarp = 4;      // 2 in the 3xTF32 configuration (its doubled stages need the room)
+constexpr int kEpiBufsPerWarp = 2;      // 2 x 4 KB staging per epilogue warp: leaves room for a 4-stage operand ring at
+                                        // BLOCK_N = 256 (TMA latency ~1 us x 96 B/clk/SM needs ~190 KB in flight)
 
 struct TileSched {
     int M, N, K;
@@ -81,7 +82,7 @@ struct Cfg {
     static constexpr int LOAD_BYTES = A_BYTES + B_BYTES;                 // bytes landed by TMA per stage
     static constexpr int STAGE_BYTES = LOAD_BYTES * (X3 ? 2 : 1);        // x3: [A_hi | B_hi | A_lo | B_lo]
     static constexpr int THREADS = kThreads + (X3 ? 128 : 0);            // x3: warps 8-11 split the operands
-    static constexpr int EPI_BUFS = X3 ? 2 : kEpiBufsPerWarp;
+    static constexpr int EPI_BUFS = kEpiBufsPerWarp;
     static constexpr int EPI_BYTES = kEpiWarps * EPI_BUFS * kEpiBufBytes;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int SMEM_LIMIT = 227 * 1024;

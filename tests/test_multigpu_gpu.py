@@ -28,7 +28,11 @@ def _build(seed, N, T, D, L, dev):
     a = types.SimpleNamespace(max_seq_len=L, embedding_dim=D, num_attention_heads=2, drop_rate=0.1, transformer_block=2,
                               num_words_title=T, num_words_abstract=0, num_words_body=0, news_attributes=["title"],
                               bert_model_load="bert_tiny", word_embedding_dim=128)
-    return a, BertModel(cfg)
+    bert = BertModel(cfg)
+    for n, p in bert.named_parameters():      # run.py:73-75 freezes the (unused) pooler; DDP then sees no unused params
+        if "pooler" in n:
+            p.requires_grad = False
+    return a, bert
 
 
 def _worker(rank, world, port, q):
