@@ -156,7 +156,7 @@ def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
     step, cores = cpu_oracle_step_fn(cfg, B_sample, seed)
     # PyTorch's CPU kernels do not always scale to every core of a big host: calibrate the thread count on one step
     best = None
-    for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+    for nt in sorted({min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
         torch.set_num_threads(nt)
         t0 = time.time()
         step()

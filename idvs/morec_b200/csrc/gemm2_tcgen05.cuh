@@ -1,0 +1,346 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM mainloop: two CTAs of a 2-CTA cluster (one TPC) cooperate on a
+// 256 x 256 output tile.  Each CTA loads its own 128 rows of A and HALF of the B tile (128 of the 256 N-rows) per
+// K-block, so the per-SM operand traffic drops from 48 KB to 32 KB per K-block (L2 -> SMEM and SMEM -> tensor core)
+// and the operand ring gets 6 stages instead of 4.  The leader CTA (cluster rank 0) issues `tcgen05.mma.cta_group::2`
+// (M = 256, N = 256) for the pair; accumulators live in both CTAs' TMEM (128 lanes x 256 columns each, double
+// buffered) and each CTA runs the epilogue for its own 128 rows.
+//
+// Synchronisation (all mbarriers; SMEM offsets are identical in both CTAs):
+//   full[s]   (leader's is used)   count 2: both producers arrive; the leader's arrive carries expect_tx of BOTH CTAs'
+//                                   bytes, and both CTAs' TMA loads complete_tx on the leader's barrier (peer bit masked)
+//   empty[s]  (per CTA)            count 1: tcgen05.commit multicast from the leader frees the slot in both CTAs
+//   tfull[a]  (per CTA)            count 1: tcgen05.commit multicast when the accumulator stage is complete
+//   tempty[a] (leader's is used)   count 2*4: every epilogue warp of BOTH CTAs arrives (remote arrive from the peer)
+#pragma once
+#include <stdlib.h>
+
+#include "gemm_tcgen05.cuh"
+
+namespace morec {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same SMEM offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(local_bar),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1) {
+    // executed by both CTAs; the peer bit of the barrier address is cleared so the bytes are credited to CTA 0
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if constexpr (KIND == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
+}
+
+template <int KIND>
+struct Cfg2 {
+    static constexpr int ELEM = KIND == 1 ? 2 : 4;
+    static constexpr int BLOCK_N = 256;                 // per pair
+    static constexpr int HALF_N = 128;                  // B rows loaded by each CTA
+    static constexpr int PAIR_M = 256;
+    static constexpr int BLOCK_K = 128 / ELEM;
+    static constexpr int UMMA_K = 32 / ELEM;
+    static constexpr int CHUNK = 128 / ELEM;
+    static constexpr int A_BYTES = BLOCK_M * 128;
+    static constexpr int B_BYTES = HALF_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // per CTA
+    static constexpr int EPI_BUFS = kEpiBufsPerWarp;
+    static constexpr int EPI_BYTES = kEpiWarps * EPI_BUFS * kEpiBufBytes;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;
+};
+
+template <int KIND, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TileSched p,
+             const typename Epi::Params ep) {
+    using C = Cfg2<KIND>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + C::STAGES;
+    uint64_t* tfull_bar = bars + 2 * C::STAGES;
+    uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmC2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 2);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull_bar[s]), 1);
+            mbar_init(smem_u32(&tempty_bar[s]), 2 * kEpiWarps);
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();                       // barrier inits of both CTAs visible before any remote arrive / TMA
+    if (warp == 2) {
+        tmem_alloc_2sm(smem_u32(tmem_slot), C::TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+    const int total_work = p.m_tiles * p.n_tiles * p.splits;      // m_tiles counts 256-row pair tiles here
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = pair; w < total_work; w += n_pairs) {
+                const int split = w % p.splits;
+                const int tile = w / p.splits;
+                const int m0 = (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M;
+                const int n0 = (tile % p.n_tiles) * C::BLOCK_N + (int)rank * C::HALF_N;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+                    else mbar_arrive_cluster(fb, 0);
+                    const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + C::A_BYTES;
+                    const int k0 = kb * C::BLOCK_K;
+                    if (!p.a_mn) {
+                        tma_load_2d_2sm(&tmA, fb, sa, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / C::CHUNK; ++c)
+                            tma_load_2d_2sm(&tmA, fb, sa + c * (C::BLOCK_K * 128), m0 + c * C::CHUNK, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d_2sm(&tmB, fb, sb, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C::HALF_N / C::CHUNK; ++c)
+                            tma_load_2d_2sm(&tmB, fb, sb + c * (C::BLOCK_K * 128), n0 + c * C::CHUNK, k0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ================================ MMA issuer (leader CTA only) ================================
+        constexpr uint32_t fmt = KIND == 1 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                               ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(C::BLOCK_N >> 3) << 17) |
+                               ((uint32_t)(C::PAIR_M >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = pair; w < total_work; w += n_pairs) {
+            const int split = w % p.splits;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * C::BLOCK_N;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k) {
+                        constexpr uint32_t mn_sbo = KIND == 1 ? 1024 : 512;
+                        constexpr uint32_t mn_lt = KIND == 1 ? 2 : 1;
+                        const uint64_t ad = p.a_mn ? make_smem_desc(sa + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
+                                                   : make_smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = p.b_mn ? make_smem_desc(sb + k * (C::UMMA_K * 128), C::BLOCK_K * 128, mn_sbo, mn_lt)
+                                                   : make_smem_desc(sb + k * 32, 16, 1024);
+                        tc_mma_2sm<KIND == 1 ? 1 : 0>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit_2sm_mc(smem_u32(&empty_bar[stage]), 3);            // slot free in both CTAs
+                    if (kb == kb1 - 1) tc_commit_2sm_mc(smem_u32(&tfull_bar[acc]), 3);   // accumulators ready in both
+                }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ epilogue (both CTAs, own 128 rows) ================================
+        const int q = warp - 4;
+        EpiStore st;
+        st.bufs = epi_base + q * (C::EPI_BUFS * kEpiBufBytes);
+        st.nsub = C::EPI_BUFS;
+        st.c_end = 0;
+        st.lane = lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = pair; w < total_work; w += n_pairs) {
+            const int split = w % p.splits;
+            const int tile = w / p.splits;
+            const int m0 = (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M;
+            const int n0 = (tile % p.n_tiles) * C::BLOCK_N;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+            Epi::template tile<C::BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::BLOCK_N, st, m0, q,
+                                           n0, split, p);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);    // leader's barrier
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait<0>();
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                       // the peer's SMEM / TMEM stay alive until the leader's MMAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int KIND, class Epi>
+int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
+    using C = Cfg2<KIND>;
+    constexpr int ELEM = C::ELEM;
+    const bool bf = KIND == 1;
+    constexpr bool SW32 = KIND != 1;
+    CUtensorMap tmA, tmB, tmC, tmC2;
+    int rc;
+    if (!g.a_mn) rc = make_tmap_2d(&tmA, g.A, bf, g.K, g.M, (uint64_t)g.lda * ELEM, C::BLOCK_K, BLOCK_M);
+    else         rc = make_tmap_2d(&tmA, g.A, bf, g.M, g.K, (uint64_t)g.lda * ELEM, C::CHUNK, C::BLOCK_K, SW32);
+    if (rc) return rc;
+    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, bf, g.K, g.N, (uint64_t)g.ldb * ELEM, C::BLOCK_K, C::HALF_N);
+    else         rc = make_tmap_2d(&tmB, g.B, bf, g.N, g.K, (uint64_t)g.ldb * ELEM, C::CHUNK, C::BLOCK_K, SW32);
+    if (rc) return rc;
+    const int out_elem = g.out_bf16 ? 2 : 4;
+    const int out_cols = 128 / out_elem;
+    if (g.C) {
+        rc = make_tmap_2d(&tmC, g.C, g.out_bf16 != 0, g.N, g.M, (uint64_t)g.ldc * out_elem, out_cols, 32);
+        if (rc) return rc;
+    } else {
+        tmC = tmA;
+    }
+    if (g.C2) {
+        rc = make_tmap_2d(&tmC2, g.C2, g.out_bf16 != 0, g.N, g.M, (uint64_t)g.ldc * out_elem, out_cols, 32);
+        if (rc) return rc;
+    } else {
+        tmC2 = tmC;
+    }
+    TileSched p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.num_kb = (g.K + C::BLOCK_K - 1) / C::BLOCK_K;
+    p.m_tiles = (g.M + C::PAIR_M - 1) / C::PAIR_M;
+    p.n_tiles = (g.N + C::BLOCK_N - 1) / C::BLOCK_N;
+    p.a_mn = g.a_mn; p.b_mn = g.b_mn;
+    p.accumulate = g.accumulate;
+    p.out_bf16 = g.out_bf16;
+    const int pairs_max = num_sms() / 2;
+    int splits = 1;
+    if (g.accumulate && g.allow_split_k) {
+        const int tiles = p.m_tiles * p.n_tiles;
+        splits = pairs_max / tiles;
+        if (splits < 1) splits = 1;
+        const int max_splits = p.num_kb / 8 > 0 ? p.num_kb / 8 : 1;
+        if (splits > max_splits) splits = max_splits;
+    }
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    const int total = p.m_tiles * p.n_tiles * p.splits;
+    const int pairs = total < pairs_max ? total : pairs_max;
+    auto kern = gemm2_kernel<KIND, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<2 * pairs, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+// Picks the CTA-pair kernel for large, wide problems (fp32/tf32 one-pass and bf16); everything else -- 3xTF32, narrow
+// N, small M -- runs on the single-CTA kernel.  MOREC_GEMM2=0 in the environment disables the pair kernel.
+inline bool gemm2_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOREC_GEMM2");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <class Epi>
+int gemm_dispatch_auto(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
+    if (gemm2_enabled() && g.dtype != 2 && gemm_is_wide(g.N) && g.M >= 512 && g.M > 0 && g.N > 0 && g.K > 0) {
+        if (g.dtype == 0) return gemm2_launch<0, Epi>(g, ep, stream);
+        if (g.dtype == 1) return gemm2_launch<1, Epi>(g, ep, stream);
+    }
+    return gemm_dispatch<Epi>(g, ep, stream);
+}
+
+}  // namespace morec

@@ -1,5 +1,5 @@
 // Standard epilogue family of the tcgen05 GEMM + the C-ABI entry point morec_gemm (see include/morec_b200.h).
-#include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 
 #include <mutex>
 
@@ -209,5 +209,5 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
     StdEpi::Params ep;
     ep.mode = epilogue; ep.alpha = alpha; ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux;
     ep.aux_bf16 = (dtype == 1);
-    return gemm_dispatch<StdEpi>(g, ep, (cudaStream_t)stream);
+    return gemm_dispatch_auto<StdEpi>(g, ep, (cudaStream_t)stream);
 }

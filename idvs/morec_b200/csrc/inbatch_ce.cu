@@ -14,7 +14,7 @@
 //   4. backward: the same GEMM with the dlogits epilogue writes dS = (softmax - onehot) * valid * g / n_valid, then
 //      dP = dS.E and dE = dS^T.P run on the standard GEMM (MN-major operands, no transposes).
 #include "../../../include/morec_b200.h"
-#include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 
 namespace morec {
 
@@ -234,7 +234,7 @@ extern "C" int morec_inbatch_ce_fwd(const void* P, const void* E, const uint32_t
     CeParams ep{};
     ep.member = member; ep.pad = pad; ep.log_pop = log_pop; ep.L = L; ep.Wc = (C + 31) / 32; ep.col_offset = col_offset;
     ep.part_m = part_m; ep.part_l = part_l; ep.tgt_logit = tgt_logit; ep.NT = ce_tiles(C, dtype);
-    if (int rc = gemm_dispatch<CeFwdEpi>(g, ep, (cudaStream_t)stream)) return rc;
+    if (int rc = gemm_dispatch_auto<CeFwdEpi>(g, ep, (cudaStream_t)stream)) return rc;
     inbatch_ce_combine_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(part_m, part_l, tgt_logit, log_mask, row_lse,
                                                                    row_loss, sum_cnt, loss, R, ep.NT);
     MOREC_LAUNCH_CHECK();
@@ -254,5 +254,5 @@ extern "C" int morec_inbatch_ce_dlogits(const void* P, const void* E, const uint
     CeParams ep{};
     ep.member = member; ep.pad = pad; ep.log_pop = log_pop; ep.L = L; ep.Wc = (C + 31) / 32; ep.col_offset = col_offset;
     ep.row_lse = row_lse; ep.log_mask = log_mask; ep.grad_out = grad_out; ep.n_valid = n_valid;
-    return gemm_dispatch<CeBwdEpi>(g, ep, (cudaStream_t)stream);
+    return gemm_dispatch_auto<CeBwdEpi>(g, ep, (cudaStream_t)stream);
 }
