@@ -229,7 +229,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="morec", choices=["morec", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "bf16"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--parallel", default="global", choices=["global", "local"],
                     help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
