@@ -27,9 +27,15 @@ extern "C" int morec_bert_layer_fwd(const MorecBertLayerFwd* a, void* stream) {
     RUN(morec_gemm(a->x, a->wqkv, a->qkv, nullptr, a->bqkv, nullptr, M, 3 * H, H, H, H, 3 * H, 0, 0, 0, a->dtype, obf,
                    MOREC_EPI_LINEAR, 1.f, 0, stream));
     const char* q = (const char*)a->qkv;
-    RUN(morec_attn_fwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->ctx, a->cu_seqlens, nullptr, 0, a->n_seq,
-                       a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, -1e9f, st, a->p_attn, a->seed,
-                       a->off_attn, stream));
+    if (a->max_len <= 32) {
+        RUN(morec_attn_fwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->ctx, a->cu_seqlens, nullptr, 0, a->n_seq,
+                           a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, -1e9f, st, a->p_attn, a->seed,
+                           a->off_attn, stream));
+    } else {   // long titles (cfg-2: T = 128): general kernel, one CTA per (sequence, head)
+        RUN(morec_attn_gen_fwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->ctx, a->cu_seqlens, nullptr, nullptr, 0,
+                               a->n_seq, a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, st, a->p_attn,
+                               a->seed, a->off_attn, stream));
+    }
     RUN(morec_gemm(a->ctx, a->w_ao, a->tmp_h, nullptr, a->b_ao, nullptr, M, H, H, H, H, H, 0, 0, 0, a->dtype, obf,
                    MOREC_EPI_LINEAR, 1.f, 0, stream));
     RUN(morec_layernorm_fwd(a->tmp_h, a->x, nullptr, 0, a->g1, a->b1, a->x1, nullptr, a->rstd1, M, H, a->eps, st,
@@ -78,9 +84,16 @@ extern "C" int morec_bert_layer_bwd(const MorecBertLayerBwd* a, void* stream) {
     // ---- attention core
     const char* q = (const char*)f->qkv;
     char* dq = (char*)a->dqkv;
-    RUN(morec_attn_bwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->dctx, dq, dq + (size_t)H * es,
-                       dq + (size_t)2 * H * es, f->cu_seqlens, nullptr, 0, f->n_seq, f->max_len, f->n_heads,
-                       H / f->n_heads, 3 * H, H, scale, -1e9f, st, f->p_attn, f->seed, f->off_attn, stream));
+    if (f->max_len <= 32) {
+        RUN(morec_attn_bwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->dctx, dq, dq + (size_t)H * es,
+                           dq + (size_t)2 * H * es, f->cu_seqlens, nullptr, 0, f->n_seq, f->max_len, f->n_heads,
+                           H / f->n_heads, 3 * H, H, scale, -1e9f, st, f->p_attn, f->seed, f->off_attn, stream));
+    } else {
+        RUN(morec_attn_gen_bwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->dctx, dq, dq + (size_t)H * es,
+                               dq + (size_t)2 * H * es, nullptr, f->cu_seqlens, nullptr, nullptr, 0, f->n_seq,
+                               f->max_len, f->n_heads, H / f->n_heads, 3 * H, H, scale, st, f->p_attn, f->seed,
+                               f->off_attn, stream));
+    }
     // ---- fused QKV projection: dWqkv, dbqkv, dx (second part of the layer-input gradient; the first is dz1)
     RUN(morec_gemm(a->dqkv, f->x, a->dwqkv, nullptr, nullptr, nullptr, 3 * H, H, M, 3 * H, H, H, 0, 1, 1, f->dtype, 0,
                    MOREC_EPI_LINEAR, 1.f, 1, stream));

@@ -100,6 +100,43 @@ __global__ void scatter_add_rows_kernel(const TS* __restrict__ src, const int32_
     }
 }
 
+// ---------------------------------------------------------------------------------------------- scaled row add / pooling
+// out[r] = (x ? x[r] : 0) + alpha * (gscale ? gscale[r / rows_per_group] : 1) * y[idx ? idx[r] : r]
+template <typename T>
+__global__ void scale_add_rows_kernel(const T* __restrict__ x, const T* __restrict__ y, const int32_t* __restrict__ idx,
+                                      const float* __restrict__ gscale, int rows_per_group, float alpha,
+                                      T* __restrict__ out, int n, int H, int ld_y) {
+    const int nv = H >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / nv), c = (int)(i - (size_t)r * nv) * 4;
+        const int sr = idx ? idx[r] : r;
+        const float sc = alpha * (gscale ? gscale[r / rows_per_group] : 1.f);
+        float4 v = sr >= 0 ? ld4<T>(y + (size_t)sr * ld_y + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        if (x) { const float4 a = ld4<T>(x + (size_t)r * H + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        st4<T>(out + (size_t)r * H + c, v);
+    }
+}
+
+// out[g] = mean over the rows_per_group consecutive rows of group g
+template <typename T>
+__global__ void mean_rows_kernel(const T* __restrict__ x, T* __restrict__ out, int n_groups, int rows_per_group, int H) {
+    const int nv = H >> 2;
+    const float inv = 1.f / rows_per_group;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_groups * nv;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / nv), c = (int)(i - (size_t)g * nv) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < rows_per_group; ++r) {
+            const float4 v = ld4<T>(x + ((size_t)g * rows_per_group + r) * H + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        st4<T>(out + (size_t)g * H + c, acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- column sum
 // out[n] += sum_m x[m, n]; CTA = 32 x 8 threads: each thread owns 4 columns, 8 row groups; grid-stride over rows.
 template <typename T>
@@ -304,6 +341,31 @@ extern "C" int morec_scatter_add_rows(const void* src, const int32_t* idx, float
     const int g = grid_for((size_t)n * (H / 4), 256);
     if (src_dtype == 0) scatter_add_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, idx, dst, n, H, ld_src, ld_dst);
     else scatter_add_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, idx, dst, n, H, ld_src, ld_dst);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_scale_add_rows(const void* x, const void* y, const int32_t* idx, const float* group_scale,
+                                    int rows_per_group, float alpha, void* out, int n, int H, int ld_y, int dtype,
+                                    void* stream) {
+    MOREC_CHECK_ARG(y && out, "scale_add_rows: null pointer");
+    MOREC_CHECK_ARG(H % 4 == 0 && ld_y % 4 == 0, "scale_add_rows: H/ld must be multiples of 4");
+    if (n <= 0) return MOREC_OK;
+    if (rows_per_group <= 0) rows_per_group = 1;
+    const int g = grid_for((size_t)n * (H / 4), 256);
+    if (dtype == 0) scale_add_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, idx, group_scale, rows_per_group, alpha, (float*)out, n, H, ld_y);
+    else scale_add_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, idx, group_scale, rows_per_group, alpha, (__nv_bfloat16*)out, n, H, ld_y);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_mean_rows(const void* x, void* out, int n_groups, int rows_per_group, int H, int dtype, void* stream) {
+    MOREC_CHECK_ARG(x && out, "mean_rows: null pointer");
+    MOREC_CHECK_ARG(H % 4 == 0 && rows_per_group > 0, "mean_rows: bad shape");
+    if (n_groups <= 0) return MOREC_OK;
+    const int g = grid_for((size_t)n_groups * (H / 4), 256);
+    if (dtype == 0) mean_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)out, n_groups, rows_per_group, H);
+    else mean_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n_groups, rows_per_group, H);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

@@ -53,6 +53,10 @@ def load():
         "morec_cast_f32_to_bf16": [P, P, L, P],
         "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
         "morec_clock_probe": [P, P],
+        "morec_attn_gen_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, I, F, U, U, P],
+        "morec_attn_gen_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, I, F, U, U, P],
+        "morec_scale_add_rows": [P, P, P, P, I, F, P, I, I, I, I, P],
+        "morec_mean_rows": [P, P, I, I, I, I, P],
         "morec_bert_layer_fwd": [P, P],
         "morec_bert_layer_bwd": [P, P],
     }
@@ -353,6 +357,47 @@ def attn_bwd(q, k, v, do, dq, dk, dv, *, cu_seqlens=None, key_mask=None, causal=
                                head_dim, q.stride(0), do.stride(0), scale, masked_add,
                                dtype_code(q), dropout_p, _u64(seed), _u64(offset), _stream())
     _check(rc, "morec_attn_bwd")
+
+
+def attn_gen_fwd(q, k, v, o, *, cu_seqlens=None, bias=None, mask=None, n_seq, seqlen, n_heads, head_dim, scale,
+                 dropout_p=0.0, seed=0, offset=0):
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    rc = load().morec_attn_gen_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(bias), _ptr(mask),
+                                   (mask.shape[0] if mask is not None else 0), n_seq, seqlen, n_heads, head_dim,
+                                   q.stride(0), o.stride(0), scale, dtype_code(q), dropout_p, _u64(seed), _u64(offset),
+                                   _stream())
+    _check(rc, "morec_attn_gen_fwd")
+    return o
+
+
+def attn_gen_bwd(q, k, v, do, dq, dk, dv, *, dbias=None, cu_seqlens=None, bias=None, mask=None, n_seq, seqlen, n_heads,
+                 head_dim, scale, dropout_p=0.0, seed=0, offset=0):
+    assert q.stride(0) == k.stride(0) == v.stride(0) == dq.stride(0) == dk.stride(0) == dv.stride(0)
+    rc = load().morec_attn_gen_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dbias),
+                                   _ptr(cu_seqlens), _ptr(bias), _ptr(mask), (mask.shape[0] if mask is not None else 0),
+                                   n_seq, seqlen, n_heads, head_dim, q.stride(0), do.stride(0), scale, dtype_code(q),
+                                   dropout_p, _u64(seed), _u64(offset), _stream())
+    _check(rc, "morec_attn_gen_bwd")
+
+
+def scale_add_rows(y, *, x=None, idx=None, group_scale=None, rows_per_group=1, alpha=1.0, out=None):
+    """out[r] = (x[r] or 0) + alpha * group_scale[r // rows_per_group] * y[idx[r] or r]"""
+    n = idx.numel() if idx is not None else (x.shape[0] if x is not None else y.shape[0])
+    H = y.shape[1]
+    if out is None:
+        out = torch.empty(n, H, device=y.device, dtype=y.dtype)
+    rc = load().morec_scale_add_rows(_ptr(x), _ptr(y), _ptr(idx), _ptr(group_scale), rows_per_group, alpha, _ptr(out), n, H,
+                                     y.stride(0), dtype_code(y), _stream())
+    _check(rc, "morec_scale_add_rows")
+    return out
+
+
+def mean_rows(x, n_groups, rows_per_group):
+    H = x.shape[1]
+    out = torch.empty(n_groups, H, device=x.device, dtype=x.dtype)
+    rc = load().morec_mean_rows(_ptr(x), _ptr(out), n_groups, rows_per_group, H, dtype_code(x), _stream())
+    _check(rc, "morec_mean_rows")
+    return out
 
 
 def inbatch_mask(row_ids, col_ids, B, L):

@@ -254,9 +254,10 @@ class BertTowerFn(torch.autograd.Function):
             else:
                 qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
                 ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
-                lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq,
-                             seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn,
-                             seed=drop.seed, offset=drop.off(1 + 4 * l))
+                (lib.attn_fwd if max_len <= 32 else lib.attn_gen_fwd)(
+                    qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len,
+                    n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn, seed=drop.seed,
+                    offset=drop.off(1 + 4 * l))
                 ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
                 x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
                                                  seed=drop.seed, off_pre=drop.off(2 + 4 * l))
@@ -392,9 +393,10 @@ class BertTowerFn(torch.autograd.Function):
                 del dao
             # attention core
             dqkv = torch.empty_like(qkv)
-            lib.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
-                         cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale,
-                         dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
+            (lib.attn_bwd if max_len <= 32 else lib.attn_gen_bwd)(
+                qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], dctx, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+                cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len, n_heads=n_heads, head_dim=dh, scale=scale,
+                dropout_p=drop.p_attn, seed=drop.seed, offset=drop.off(1 + 4 * l))
             del dctx
             # fused QKV projection backward
             lib.linear_wgrad(dqkv, x, dwqkv)

@@ -95,6 +95,21 @@ int morec_attn_bwd(const void* q, const void* k, const void* v, const void* d_o,
                    int head_dim, int ld, int ld_o, float scale, float masked_add, int dtype, float dropout_p,
                    uint64_t seed, uint64_t offset, void* stream);
 
+/* ---- general attention, sequences / windows of up to 128 tokens, optional additive bias and mask ----------------
+ * Swin window attention (HF SwinSelfAttention; call site inbatch_sasrec_e2e_vision/model/encoders.py:31): L = 49,
+ * bias[n_heads, L, L] = relative-position bias gathered by the caller, mask[n_mask, L, L] = shifted-window mask
+ * (0 / -100; window s uses mask s % n_mask); and BERT with long titles (cfg-2, T = 128) packed by cu_seqlens.
+ * score = q.k * scale + bias + mask; dropout on the probabilities; backward also accumulates dbias (fp32, atomics).
+ */
+int morec_attn_gen_fwd(const void* q, const void* k, const void* v, void* o, const int32_t* cu_seqlens,
+                       const float* bias, const float* mask, int n_mask, int n_seq, int seqlen, int n_heads,
+                       int head_dim, int ld, int ld_o, float scale, int dtype, float dropout_p, uint64_t seed,
+                       uint64_t offset, void* stream);
+int morec_attn_gen_bwd(const void* q, const void* k, const void* v, const void* d_o, void* dq, void* dk, void* dv,
+                       float* dbias, const int32_t* cu_seqlens, const float* bias, const float* mask, int n_mask,
+                       int n_seq, int seqlen, int n_heads, int head_dim, int ld, int ld_o, float scale, int dtype,
+                       float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+
 /* ---- in-batch debiased softmax cross-entropy (model/model.py:45-67) ---------------------------
  * morec_inbatch_mask   : integer pre-pass.  member[B, ceil(C/32)] bit c = (col_ids[c] in row_ids[b, 0..L]);
  *                        pad[ceil(C/32)] bit c = (col_ids[c] == 0).  Bit-exact restatement of model.py:51-63.
@@ -135,6 +150,13 @@ int morec_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int
 int morec_scatter_add_rows(const void* src, const int32_t* idx, float* dst, int n, int H, int ld_src, int ld_dst,
                            int src_dtype, void* stream);
 int morec_colsum(const void* x, float* out, int M, int N, int ld, int dtype, void* stream);
+/* out[r] = (x ? x[r] : 0) + alpha * (group_scale ? group_scale[r / rows_per_group] : 1) * y[idx ? idx[r] : r]
+ * (residual add of a window-permuted branch with per-image drop-path scale: HF SwinLayer.forward; its backward;
+ * broadcast backward of the mean pool).  idx[r] < 0 contributes 0. */
+int morec_scale_add_rows(const void* x, const void* y, const int32_t* idx, const float* group_scale, int rows_per_group,
+                         float alpha, void* out, int n, int H, int ld_y, int dtype, void* stream);
+/* out[g] = mean of rows [g*rows_per_group, (g+1)*rows_per_group)   (HF SwinModel AdaptiveAvgPool1d over 49 tokens) */
+int morec_mean_rows(const void* x, void* out, int n_groups, int rows_per_group, int H, int dtype, void* stream);
 /* out = dy * act'(aux): mode 0 = erf-GELU with aux = pre-activation (encoders.py:70), 1 = ReLU with aux = output */
 int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mode, int dtype, void* stream);
 int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

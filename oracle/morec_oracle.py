@@ -246,27 +246,41 @@ class StepOut:
     n_valid: int
 
 
-def model_forward(p: Dict[str, torch.Tensor], ids: torch.Tensor, items: torch.Tensor,
-                  log_mask: torch.Tensor, pop_prob: torch.Tensor, *, use_modal: bool,
-                  n_heads_user: int, n_heads_bert: int = 0) -> StepOut:
-    """Full Model.forward (model/model.py:31-69) in eval mode.
-
-    ids [B, L+1] int64; items [C, 2T] int64 (modal) or [C] int64 (ID); log_mask [B, L]; pop_prob [N+1].
-    """
+def model_forward_from_embs(p: Dict[str, torch.Tensor], E: torch.Tensor, ids: torch.Tensor, log_mask: torch.Tensor,
+                            pop_prob: torch.Tensor, n_heads_user: int) -> StepOut:
+    """Model.forward after the item tower (model/model.py:39-69): E [C, D] are the slot embeddings."""
     B, Lp1 = ids.shape
     L = Lp1 - 1
-    dt = next(iter(p.values())).dtype
-    log_pop = torch.log(pop_prob.to(torch.float32)[ids.reshape(-1)]).to(dt)     # FloatTensor in the reference
-    if use_modal:
-        E = text_item_encoder(p, items, n_heads_bert)
-    else:
-        E = p["id_embedding.weight"][items.reshape(-1)]
+    log_pop = torch.log(pop_prob.to(torch.float32)[ids.reshape(-1)]).to(E.dtype)   # FloatTensor in the reference
     D = E.shape[1]
     X = E.view(B, Lp1, D)[:, :-1, :]
     Hh = sasrec_forward(p, X, log_mask, n_heads_user)
     P = Hh.reshape(B * L, D)
     loss, S, lse, n_valid = inbatch_ce(P, E, ids, log_pop, log_mask)
     return StepOut(loss, S, E, P, n_valid)
+
+
+def model_forward(p: Dict[str, torch.Tensor], ids: torch.Tensor, items: torch.Tensor,
+                  log_mask: torch.Tensor, pop_prob: torch.Tensor, *, use_modal: bool,
+                  n_heads_user: int, n_heads_bert: int = 0) -> StepOut:
+    """Full Model.forward of the TEXT package (model/model.py:31-69) in eval mode.
+
+    ids [B, L+1] int64; items [C, 2T] int64 (modal) or [C] int64 (ID); log_mask [B, L]; pop_prob [N+1].
+    """
+    if use_modal:
+        E = text_item_encoder(p, items, n_heads_bert)
+    else:
+        E = p["id_embedding.weight"][items.reshape(-1)]
+    return model_forward_from_embs(p, E, ids, log_mask, pop_prob, n_heads_user)
+
+
+def vision_item_encoder(image_net, images: torch.Tensor) -> torch.Tensor:
+    """Vit_Encoder.forward (inbatch_sasrec_e2e_vision/model/encoders.py:30-31): GELU(image_net(pixel_values)[0]).
+
+    `image_net` is the third-party HF SwinForImageClassification itself (the reference calls exactly this module,
+    inbatch_sasrec_e2e_vision/run.py:49); it is installed on the GPU box too, so the oracle calls it directly on CPU
+    instead of restating ~400 lines of modeling_swin.py.  Pinned by tests/golden/vision_tiny.pt (reference output)."""
+    return gelu_erf(image_net(images)[0])
 
 
 # --------------------------------------------------------------------------------------------------

@@ -341,3 +341,81 @@ def test_adamw_multi_matches_torch(lib):
         fo.step()
     for r, m in zip(ref, mine):
         assert torch.allclose(r, m, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_heads,dh,L,bias,n_mask", [(3, 32, 49, True, 4), (2, 64, 128, False, 0), (12, 32, 49, True, 0), (2, 64, 40, False, 0)])
+def test_attention_general_bias_mask(lib, n_heads, dh, L, bias, n_mask):
+    """general (<= 128 token) attention: Swin-style windows with relative-position bias + shift mask, long BERT titles"""
+    torch.manual_seed(L + dh)
+    nW, H = 13, n_heads * dh
+    qkv = torch.randn(nW * L, 3 * H, device="cuda") * 0.5
+    B = (torch.randn(n_heads, L, L, device="cuda") * 0.3) if bias else None
+    Mk = None
+    if n_mask:
+        Mk = torch.where(torch.rand(n_mask, L, L, device="cuda") > 0.7, -100.0, 0.0)
+        Mk[:, torch.arange(L), torch.arange(L)] = 0.0
+    scale = 1 / math.sqrt(dh)
+    o = torch.empty(nW * L, H, device="cuda")
+    lib.attn_gen_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, bias=B, mask=Mk, n_seq=nW, seqlen=L, n_heads=n_heads,
+                     head_dim=dh, scale=scale)
+    qd = qkv.double().requires_grad_(True)
+    Bd = B.double().requires_grad_(True) if bias else None
+    add = torch.zeros(nW, n_heads, L, L, device="cuda", dtype=torch.double)
+    if bias:
+        add = add + Bd.unsqueeze(0)
+    if n_mask:
+        add = add + Mk.double()[torch.arange(nW, device="cuda") % n_mask].unsqueeze(1)
+    q = qd[:, :H].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    k = qd[:, H:2 * H].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    v = qd[:, 2 * H:].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * scale + add, -1) @ v).transpose(1, 2).reshape(nW * L, H)
+    assert rel(o, ref) < 2e-5
+    do = torch.randn(nW * L, H, device="cuda")
+    ref.backward(do.double())
+    dqkv = torch.empty_like(qkv)
+    dB = torch.zeros(n_heads, L, L, device="cuda") if bias else None
+    lib.attn_gen_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], dbias=dB,
+                     bias=B, mask=Mk, n_seq=nW, seqlen=L, n_heads=n_heads, head_dim=dh, scale=scale)
+    assert rel(dqkv, qd.grad) < 5e-5
+    if bias:
+        assert rel(dB, Bd.grad) < 5e-5
+
+
+def test_attention_general_packed_long(lib):
+    torch.manual_seed(9)
+    n_heads, dh, T = 2, 64, 128
+    H = n_heads * dh
+    lens = torch.tensor([128, 6, 77, 33, 1, 100])
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    n_tok = int(cu[-1])
+    qkv = torch.randn(n_tok, 3 * H, device="cuda")
+    o = torch.empty(n_tok, H, device="cuda")
+    scale = 1 / math.sqrt(dh)
+    lib.attn_gen_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, cu_seqlens=cu.cuda(), n_seq=len(lens), seqlen=T,
+                     n_heads=n_heads, head_dim=dh, scale=scale)
+    do = torch.randn(n_tok, H, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    lib.attn_gen_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+                     cu_seqlens=cu.cuda(), n_seq=len(lens), seqlen=T, n_heads=n_heads, head_dim=dh, scale=scale)
+    for s in range(len(lens)):
+        a, b = int(cu[s]), int(cu[s + 1])
+        x = qkv[a:b].double().requires_grad_(True)
+        n = b - a
+        ref = _ref_attn(x[:, :H].reshape(1, n, H), x[:, H:2 * H].reshape(1, n, H), x[:, 2 * H:].reshape(1, n, H), n_heads, scale,
+                        torch.zeros(1, 1, n, n, device="cuda", dtype=torch.double)).reshape(n, H)
+        assert rel(o[a:b], ref) < 2e-5
+        ref.backward(do[a:b].double())
+        assert rel(dqkv[a:b], x.grad) < 5e-5
+
+
+def test_scale_add_and_mean_rows(lib):
+    torch.manual_seed(11)
+    n, H, rpg = 98, 64, 49
+    x = torch.randn(n, H, device="cuda"); y = torch.randn(n, H, device="cuda")
+    perm = torch.randperm(n, device="cuda").to(torch.int32)
+    gs = torch.tensor([0.0, 1.0 / 0.9], device="cuda")
+    out = lib.scale_add_rows(y, x=x, idx=perm, group_scale=gs, rows_per_group=rpg)
+    ref = x + gs.repeat_interleave(rpg).view(-1, 1) * y[perm.long()]
+    assert torch.allclose(out, ref, atol=1e-6)
+    assert torch.allclose(lib.mean_rows(x, 2, rpg), x.view(2, rpg, H).mean(1), atol=1e-6)

@@ -110,3 +110,36 @@ def test_synth_batch_properties():
     assert it.shape == (16 * 26, 60)
     assert (it[ids.reshape(-1) == 0] == 0).all()
     assert (it[ids.reshape(-1) != 0, 0] == 101).all()
+
+
+def _vision_oracle(g, grad=False):
+    from transformers import SwinConfig, SwinForImageClassification
+    m = g["meta"]
+    net = SwinForImageClassification(SwinConfig(**m["swin_cfg"]))
+    net.classifier = torch.nn.Linear(net.classifier.in_features, m["D"])
+    sd = g["state_dict"]
+    net.load_state_dict({k[len("cv_encoder.image_net."):]: v for k, v in sd.items() if k.startswith("cv_encoder.image_net.")})
+    net.eval()
+    p = {k: v.clone().requires_grad_(grad) for k, v in sd.items() if k.startswith("user_encoder.")}
+    if not grad:
+        with torch.no_grad():
+            E = O.vision_item_encoder(net, g["images"])
+    else:
+        E = O.vision_item_encoder(net, g["images"])
+    return net, p, O.model_forward_from_embs(p, E, g["ids"], g["log_mask"], g["pop_prob"], m["heads"])
+
+
+def test_vision_oracle_matches_reference():
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vision_tiny.pt"), map_location="cpu", weights_only=False)
+    net, p, out = _vision_oracle(g, grad=True)
+    assert abs(float(out.loss) - float(g["loss"])) <= 1e-5
+    assert torch.allclose(out.score_embs, g["score_embs"], atol=2e-5)
+    out.loss.backward()
+    for k, gref in g["grads"].items():
+        if k.startswith("cv_encoder.image_net."):
+            got = dict(net.named_parameters())[k[len("cv_encoder.image_net."):]].grad
+        else:
+            got = p[k].grad
+        assert got is not None, k
+        assert float((got - gref).abs().max()) <= 2e-4 * (float(gref.abs().max()) + 1e-12) + 1e-7, k

@@ -158,3 +158,65 @@ def test_bert_base_shape_vs_oracle():
     assert abs(float(loss) - float(out.loss)) <= 1e-3, (float(loss), float(out.loss))
     nonpad = d["ids"].reshape(-1) != 0
     assert float((cap["E"].detach().cpu().float()[nonpad] - out.score_embs[nonpad]).abs().max()) <= 1e-3
+
+
+def _build_vision(g):
+    from transformers import SwinConfig, SwinForImageClassification
+    from idvs.morec_b200.model_vision import Model
+    m = g["meta"]
+    net = SwinForImageClassification(SwinConfig(**m["swin_cfg"]))
+    net.classifier = torch.nn.Linear(net.classifier.in_features, m["D"])
+    a = types.SimpleNamespace(max_seq_len=m["L"], embedding_dim=m["D"], num_attention_heads=m["heads"], drop_rate=0.1,
+                              transformer_block=m["blocks"], CV_model_load="swin_tiny")
+    model = Model(a, m["N"], True, net, g["pop_prob"].numpy())
+    missing, unexpected = model.load_state_dict(g["state_dict"], strict=False)
+    assert not unexpected and not [k for k in missing if "relative_position_index" not in k], (missing, unexpected)
+    return model.cuda().eval()
+
+
+@pytest.mark.parametrize("dedup", ["auto", "slots"])
+def test_vision_step_matches_reference_golden(dedup):
+    """SASRec + Swin tower (2 stages, shifted windows, patch merging) vs the unmodified reference vision Model."""
+    import os
+    from oracle import morec_oracle as O
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vision_tiny.pt"), map_location="cpu", weights_only=False)
+    model = _build_vision(g)
+    model.item_dedup = dedup
+    cap = {}
+    orig = model._encode_items
+    model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+    model.zero_grad()
+    loss = model(g["ids"].reshape(-1).cuda(), g["images"].cuda(), g["log_mask"].cuda(), 0)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-3, (float(loss), float(g["loss"]))
+    nonpad = g["ids"].reshape(-1) != 0
+    E = cap["E"].detach().cpu().float()
+    assert float((E[nonpad] - g["score_embs"][nonpad]).abs().max()) <= 2e-3
+    grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+    for k, gref in g["grads"].items():
+        assert k in grads, k
+        scale = float(gref.abs().max()) + 1e-12
+        assert float((grads[k] - gref).abs().max()) <= 2e-2 * scale + 1e-7, k
+
+
+def test_bert_long_titles_cfg2_shape_vs_oracle():
+    """cfg-2: BERT-tiny text tower with T = 128 word pieces (general attention kernel) vs the CPU oracle."""
+    from transformers import BertConfig, BertModel
+    from oracle import morec_oracle as O
+    from idvs.morec_b200.model import Model
+    from idvs.morec_b200.synth import synth_batch
+    torch.manual_seed(6)
+    B, L, N, T, D = 4, 6, 60, 128, 64
+    d = synth_batch(B, L, N, T, seed=6, modal=True, n_users_pop=100, vocab_lo=10, vocab_hi=900)
+    bert = BertModel(BertConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+                                vocab_size=1024, max_position_embeddings=512))
+    a = types.SimpleNamespace(max_seq_len=L, embedding_dim=D, num_attention_heads=2, drop_rate=0.1, transformer_block=2,
+                              num_words_title=T, num_words_abstract=0, num_words_body=0, news_attributes=["title"],
+                              bert_model_load="bert_tiny", word_embedding_dim=128)
+    model = Model(a, N, True, bert, d["pop_prob"].numpy()).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    out = O.model_forward(sd, d["ids"], d["items"], d["log_mask"], d["pop_prob"], use_modal=True, n_heads_user=2, n_heads_bert=2)
+    model = model.cuda()
+    loss = model(d["ids"].reshape(-1).cuda(), d["items"].cuda(), d["log_mask"].cuda(), 0)
+    loss.backward()
+    assert abs(float(loss) - float(out.loss)) <= 1e-3, (float(loss), float(out.loss))
