@@ -35,6 +35,12 @@ BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_at
                  max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12)
 CFG = dict(B=64, L=25, T=30, D=512, heads=2, blocks=2, N=50000, drop=0.1,
            lr=1e-4, fine_tune_lr=5e-5, l2=0.01, fine_tune_l2=0.01)      # train_bert_base.py:22-28
+# BASELINE.json configs[3]: SASRec + Swin-T, HM-shape synthetic 3x224x224, B=32, L=10 (V/parameters.py:38), D=512
+SWIN_T = dict(image_size=224, patch_size=4, num_channels=3, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+              window_size=7, mlp_ratio=4.0, qkv_bias=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+              drop_path_rate=0.1, hidden_act="gelu", layer_norm_eps=1e-5)
+CFG_VISION = dict(B=32, L=10, T=0, D=512, heads=2, blocks=2, N=50000, drop=0.1,
+                  lr=1e-4, fine_tune_lr=1e-4, l2=0.1, fine_tune_l2=0.1)    # train_swin_tiny.py
 
 
 def make_args(cfg):
@@ -177,6 +183,62 @@ def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
                        f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt
 
 
+def _synth_images(ids, seed, dev=None):
+    """HM-shape synthetic item images: a deterministic randn image per item id (post-normalisation range,
+    V/data_utils/dataset.py:71), zero image for pad slots; generated per distinct id so duplicates are identical."""
+    import torch
+    flat = ids.reshape(-1)
+    uniq, inv = torch.unique(flat, return_inverse=True)
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.randn(uniq.numel(), 3, 224, 224, generator=g)
+    imgs[uniq == 0] = 0
+    return imgs[inv]
+
+
+def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global"):
+    import torch
+    from transformers import SwinConfig, SwinForImageClassification
+    from idvs.morec_b200.model_vision import Model
+    from idvs.morec_b200.optim import FusedAdamW
+    from idvs.morec_b200.synth import synth_batch
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(12345)
+    net = SwinForImageClassification(SwinConfig(**SWIN_T))
+    net.classifier = torch.nn.Linear(net.classifier.in_features, cfg["D"])          # V/run.py:49-54
+    torch.nn.init.xavier_normal_(net.classifier.weight.data)
+    torch.nn.init.constant_(net.classifier.bias.data, 0)
+    batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], 0, 777 + 1000 * rank + i, modal=False, mind_shape=False)
+               for i in range(n_batches)]
+    a = types.SimpleNamespace(max_seq_len=cfg["L"], embedding_dim=cfg["D"], num_attention_heads=cfg["heads"],
+                              drop_rate=cfg["drop"], transformer_block=cfg["blocks"], CV_model_load="swin_tiny")
+    model = Model(a, cfg["N"], True, net, batches[0]["pop_prob"].numpy()).to(dev)
+    model.set_compute_dtype(mode)
+    model.parallel_mode = "local" if world > 1 else parallel     # (global mode exchanges token rows; images stay local)
+    model.train()
+    if world > 1:
+        from idvs.morec_b200.parallel import wrap_ddp
+        model_run = wrap_ddp(model, local_rank)
+    else:
+        model_run = model
+    net_params = [p for n, p in model.named_parameters() if p.requires_grad and "image_net" in n and "classifier" not in n]
+    rec_params = [p for n, p in model.named_parameters() if p.requires_grad and not ("image_net" in n and "classifier" not in n)]
+    opt = FusedAdamW([{"params": net_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
+                      {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+    host = [(b["ids"].pin_memory(), _synth_images(b["ids"], 99 + i).pin_memory(), b["log_mask"].pin_memory())
+            for i, b in enumerate(batches)]
+    resident = [(a_.to(dev), b_.to(dev), c_.to(dev)) for (a_, b_, c_) in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step(ids, items, lm):
+        opt.zero_grad(set_to_none=True)
+        loss = model_run(ids.view(-1), items, lm, local_rank)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step, host, resident, h2d_bytes
+
+
 def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global"):
     """model + optimizer + synthetic batches exactly as the reference loop builds them (run.py:127-162);
     returns (step_fn, pinned host batches, device-resident batches, H2D bytes per step)"""
@@ -232,14 +294,19 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "bf16"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--parallel", default="global", choices=["global", "local"],
                     help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")
+    ap.add_argument("--workload", default="text", choices=["text", "vision"],
+                    help="text = SASRec+BERT-base (headline, configs[2]); vision = SASRec+Swin-T (configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-users", type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = dict(CFG)
-    workload = (f"MoRec SASRec+BERT-base end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, T={cfg['T']}, "
+    vision = args.workload == "vision"
+    cfg = dict(CFG_VISION) if vision else dict(CFG)
+    workload = (f"MoRec SASRec+Swin-T end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, 3x224x224 images, "
+                f"D={cfg['D']}, HM-shape synthetic (BASELINE.json configs[3])") if vision else \
+               (f"MoRec SASRec+BERT-base end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, T={cfg['T']}, "
                 f"D={cfg['D']}, N={cfg['N']} items, MIND-shape synthetic (BASELINE.json configs[2])")
 
     if args.impl == "reference":
@@ -266,7 +333,8 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
-    step, host, resident, h2d_bytes = setup_training(cfg, args.mode, W + K, rank, world, local_rank, args.parallel)
+    step, host, resident, h2d_bytes = (setup_training_vision if vision else setup_training)(
+        cfg, args.mode, W + K, rank, world, local_rank, args.parallel)
 
     def sync():
         if world > 1:
@@ -276,7 +344,8 @@ def main():
     # ---------------- device-resident throughput (`value`): K steps, batches already in HBM
     # warm-up: W steps, the first one on the batch with the most real tokens so the allocator reaches its
     # steady-state footprint before anything is timed
-    big = max(range(len(host)), key=lambda i: int((host[i][1].reshape(-1, 2 * cfg["T"])[:, cfg["T"]:] != 0).sum()))
+    big = 0 if vision else max(range(len(host)),
+                               key=lambda i: int((host[i][1].reshape(-1, 2 * cfg["T"])[:, cfg["T"]:] != 0).sum()))
     step(*resident[big])
     for i in range(W - 1):
         step(*resident[i])
@@ -363,7 +432,7 @@ def main():
                          "tf32": "kind::tf32 runs at half the bf16 rate: attainable fraction of the bf16 peak is 1/2",
                          "bf16": "kind::f16"}[args.mode]}
     cpu_base = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not vision:
         cpu_base, _ = time_cpu_oracle(cfg, args.cpu_sample_users, 1, 1)
     line = {"metric": "training sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -36,33 +36,70 @@ struct GenCfg {
     static constexpr int THREADS = 32 * NW;
 };
 
-template <typename T, int NW>
+
+// head-dim chunk width DC (32 for Swin's 32-wide heads, 64 otherwise): register slices and the smem tile stride
+template <typename T, int DC>
+__device__ __forceinline__ void load_row_t(float (&v)[DC], const T* row, int w, bool active) {
+#pragma unroll
+    for (int t = 0; t < DC / 4; ++t) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && 4 * t < w) x = ld4<T>(row + 4 * t);
+        v[4 * t] = x.x; v[4 * t + 1] = x.y; v[4 * t + 2] = x.z; v[4 * t + 3] = x.w;
+    }
+}
+template <typename T, int DC>
+__device__ __forceinline__ void store_row_t(T* row, const float (&v)[DC], int w) {
+#pragma unroll
+    for (int t = 0; t < DC / 4; ++t)
+        if (4 * t < w) st4<T>(row + 4 * t, make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]));
+}
+template <int DC>
+__device__ __forceinline__ void dot4keys_t(const float (&v)[DC], const float* tile, int j0, int w, float& a0, float& a1,
+                                           float& a2, float& a3) {
+    const float4* k0 = reinterpret_cast<const float4*>(tile + (j0 + 0) * DC);
+    const float4* k1 = reinterpret_cast<const float4*>(tile + (j0 + 1) * DC);
+    const float4* k2 = reinterpret_cast<const float4*>(tile + (j0 + 2) * DC);
+    const float4* k3 = reinterpret_cast<const float4*>(tile + (j0 + 3) * DC);
+    const int nt = w >> 2;
+#pragma unroll
+    for (int t = 0; t < DC / 4; ++t) {
+        if (t < nt) {
+            const float4 x0 = k0[t], x1 = k1[t], x2 = k2[t], x3 = k3[t];
+            a0 += v[4 * t] * x0.x + v[4 * t + 1] * x0.y + v[4 * t + 2] * x0.z + v[4 * t + 3] * x0.w;
+            a1 += v[4 * t] * x1.x + v[4 * t + 1] * x1.y + v[4 * t + 2] * x1.z + v[4 * t + 3] * x1.w;
+            a2 += v[4 * t] * x2.x + v[4 * t + 1] * x2.y + v[4 * t + 2] * x2.z + v[4 * t + 3] * x2.w;
+            a3 += v[4 * t] * x3.x + v[4 * t + 1] * x3.y + v[4 * t + 2] * x3.z + v[4 * t + 3] * x3.w;
+        }
+    }
+}
+
+template <typename T, int NW, int DC>
 __device__ __forceinline__ void load_tile_blk(float* tile, const T* base, int ld, int row0, int len, int col0, int w) {
     const int nv = w >> 2;
     for (int idx = threadIdx.x; idx < len * nv; idx += 32 * NW) {
         const int r = idx / nv, c = (idx - r * nv) << 2;
-        *reinterpret_cast<float4*>(tile + r * AT_DCH + c) = ld4<T>(base + (size_t)(row0 + r) * ld + col0 + c);
+        *reinterpret_cast<float4*>(tile + r * DC + c) = ld4<T>(base + (size_t)(row0 + r) * ld + col0 + c);
     }
 }
 
 // S[row][j] (+)= <x_row, tile_j> for all keys; x = this thread's row of Xb (Q or dO)
-template <typename T, int NW>
+template <typename T, int NW, int DC>
 __device__ __forceinline__ void raw_scores_blk(float* tile, float* S, const T* Xb, int ldx, const T* Kb, int ldk,
                                                int head_dim, int colh, int row0, int len) {
     using G = GenCfg<NW>;
     const int row = threadIdx.x;
     const int len4 = (len + 3) & ~3;
-    for (int dc = 0; dc < head_dim; dc += AT_DCH) {
-        const int w = min(AT_DCH, head_dim - dc);
+    for (int dc = 0; dc < head_dim; dc += DC) {
+        const int w = min(DC, head_dim - dc);
         __syncthreads();
-        load_tile_blk<T, NW>(tile, Kb, ldk, row0, len, colh + dc, w);
+        load_tile_blk<T, NW, DC>(tile, Kb, ldk, row0, len, colh + dc, w);
         __syncthreads();
-        float xv[AT_DCH];
-        load_row<T>(xv, Xb + (size_t)(row0 + (row < len ? row : 0)) * ldx + colh + dc, w, row < len);
+        float xv[DC];
+        load_row_t<T, DC>(xv, Xb + (size_t)(row0 + (row < len ? row : 0)) * ldx + colh + dc, w, row < len);
 #pragma unroll 1
         for (int j0 = 0; j0 < len4; j0 += 4) {
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            dot4keys(xv, tile, j0, w, a0, a1, a2, a3);
+            dot4keys_t<DC>(xv, tile, j0, w, a0, a1, a2, a3);
             float* sr = S + row * G::LS + j0;
             if (dc == 0) { sr[0] = a0; sr[1] = a1; sr[2] = a2; sr[3] = a3; }
             else { sr[0] += a0; sr[1] += a1; sr[2] += a2; sr[3] += a3; }
@@ -70,18 +107,18 @@ __device__ __forceinline__ void raw_scores_blk(float* tile, float* S, const T* X
     }
 }
 
-template <int NW, bool TRANSPOSED>
-__device__ __forceinline__ void weighted_rows_blk(const float* coef, const float* tile, int len, float (&acc)[AT_DCH]) {
+template <int NW, bool TRANSPOSED, int DC>
+__device__ __forceinline__ void weighted_rows_blk(const float* coef, const float* tile, int len, float (&acc)[DC]) {
     using G = GenCfg<NW>;
     const int row = threadIdx.x;
 #pragma unroll
-    for (int t = 0; t < AT_DCH; ++t) acc[t] = 0.f;
+    for (int t = 0; t < DC; ++t) acc[t] = 0.f;
 #pragma unroll 2
     for (int j = 0; j < len; ++j) {
         const float d = TRANSPOSED ? coef[j * G::LS + row] : coef[row * G::LS + j];
-        const float4* r = reinterpret_cast<const float4*>(tile + j * AT_DCH);
+        const float4* r = reinterpret_cast<const float4*>(tile + j * DC);
 #pragma unroll
-        for (int t = 0; t < AT_DCH / 4; ++t) {
+        for (int t = 0; t < DC / 4; ++t) {
             const float4 x = r[t];
             acc[4 * t] += d * x.x; acc[4 * t + 1] += d * x.y; acc[4 * t + 2] += d * x.z; acc[4 * t + 3] += d * x.w;
         }
@@ -130,12 +167,12 @@ __device__ __forceinline__ void gen_range(const GenAttnParams& p, int s, int lma
     if (len > lmax) len = lmax;
 }
 
-template <typename T, int NW>
+template <typename T, int NW, int DC>
 __global__ void __launch_bounds__(32 * NW) attn_gen_fwd_kernel(const GenAttnParams p) {
     using G = GenCfg<NW>;
     extern __shared__ __align__(16) float ag_smem[];
     float* tile = ag_smem;                       // [LMAX][64]
-    float* S = ag_smem + G::LMAX * AT_DCH;       // [LMAX][LS]
+    float* S = ag_smem + G::LMAX * DC;       // [LMAX][LS]
     const int row = threadIdx.x;
     const int h = blockIdx.y;
     const int colh = h * p.head_dim;
@@ -148,7 +185,7 @@ __global__ void __launch_bounds__(32 * NW) attn_gen_fwd_kernel(const GenAttnPara
         int row0, len;
         gen_range(p, s, G::LMAX, row0, len);
         if (len <= 0) continue;
-        raw_scores_blk<T, NW>(tile, S, Q, p.ld, K, p.ld, p.head_dim, colh, row0, len);
+        raw_scores_blk<T, NW, DC>(tile, S, Q, p.ld, K, p.ld, p.head_dim, colh, row0, len);
         softmax_row_blk<NW>(p, S, s, h, len);
         if (p.dropout_p > 0.f && row < len) {
             const float sc = 1.f / (1.f - p.dropout_p);
@@ -156,25 +193,25 @@ __global__ void __launch_bounds__(32 * NW) attn_gen_fwd_kernel(const GenAttnPara
 #pragma unroll 1
             for (int j = 0; j < len; ++j) S[row * G::LS + j] = gen_keep(p, pair, row, j, th) ? S[row * G::LS + j] * sc : 0.f;
         }
-        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {
-            const int w = min(AT_DCH, p.head_dim - dc);
+        for (int dc = 0; dc < p.head_dim; dc += DC) {
+            const int w = min(DC, p.head_dim - dc);
             __syncthreads();
-            load_tile_blk<T, NW>(tile, V, p.ld, row0, len, colh + dc, w);
+            load_tile_blk<T, NW, DC>(tile, V, p.ld, row0, len, colh + dc, w);
             __syncthreads();
-            float ov[AT_DCH];
-            weighted_rows_blk<NW, false>(S, tile, len, ov);
-            if (row < len) store_row<T>(O + (size_t)(row0 + row) * p.ld_o + colh + dc, ov, w);
+            float ov[DC];
+            weighted_rows_blk<NW, false, DC>(S, tile, len, ov);
+            if (row < len) store_row_t<T, DC>(O + (size_t)(row0 + row) * p.ld_o + colh + dc, ov, w);
         }
         __syncthreads();
     }
 }
 
-template <typename T, int NW>
+template <typename T, int NW, int DC>
 __global__ void __launch_bounds__(32 * NW) attn_gen_bwd_kernel(const GenAttnParams p) {
     using G = GenCfg<NW>;
     extern __shared__ __align__(16) float ag_smem[];
     float* tile = ag_smem;                                   // [LMAX][64]
-    float* Pm = ag_smem + G::LMAX * AT_DCH;                  // [LMAX][LS]  P, then P~
+    float* Pm = ag_smem + G::LMAX * DC;                  // [LMAX][LS]  P, then P~
     float* dSm = Pm + G::LMAX * G::LS;                       // [LMAX][LS]  dP~, then dS*scale
     float* dB = dSm + G::LMAX * G::LS;                       // [seqlen*seqlen] bias-gradient accumulator (if dbias)
     const int row = threadIdx.x;
@@ -195,9 +232,9 @@ __global__ void __launch_bounds__(32 * NW) attn_gen_bwd_kernel(const GenAttnPara
         int row0, len;
         gen_range(p, s, G::LMAX, row0, len);
         if (len <= 0) continue;
-        raw_scores_blk<T, NW>(tile, Pm, Q, p.ld, K, p.ld, p.head_dim, colh, row0, len);
+        raw_scores_blk<T, NW, DC>(tile, Pm, Q, p.ld, K, p.ld, p.head_dim, colh, row0, len);
         softmax_row_blk<NW>(p, Pm, s, h, len);
-        raw_scores_blk<T, NW>(tile, dSm, dO, p.ld_o, V, p.ld, p.head_dim, colh, row0, len);   // dP~ = dO . V^T
+        raw_scores_blk<T, NW, DC>(tile, dSm, dO, p.ld_o, V, p.ld, p.head_dim, colh, row0, len);   // dP~ = dO . V^T
         {
             const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
             const int pair = s * p.n_heads + h;
@@ -223,32 +260,32 @@ __global__ void __launch_bounds__(32 * NW) attn_gen_bwd_kernel(const GenAttnPara
             }
         }
         __syncthreads();
-        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {      // dQ_i = sum_j dS_ij K_j
-            const int w = min(AT_DCH, p.head_dim - dc);
+        for (int dc = 0; dc < p.head_dim; dc += DC) {      // dQ_i = sum_j dS_ij K_j
+            const int w = min(DC, p.head_dim - dc);
             __syncthreads();
-            load_tile_blk<T, NW>(tile, K, p.ld, row0, len, colh + dc, w);
+            load_tile_blk<T, NW, DC>(tile, K, p.ld, row0, len, colh + dc, w);
             __syncthreads();
-            float acc[AT_DCH];
-            weighted_rows_blk<NW, false>(dSm, tile, len, acc);
-            if (row < len) store_row<T>(dQ + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
+            float acc[DC];
+            weighted_rows_blk<NW, false, DC>(dSm, tile, len, acc);
+            if (row < len) store_row_t<T, DC>(dQ + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
         }
-        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {      // dK_j = sum_i dS_ij Q_i
-            const int w = min(AT_DCH, p.head_dim - dc);
+        for (int dc = 0; dc < p.head_dim; dc += DC) {      // dK_j = sum_i dS_ij Q_i
+            const int w = min(DC, p.head_dim - dc);
             __syncthreads();
-            load_tile_blk<T, NW>(tile, Q, p.ld, row0, len, colh + dc, w);
+            load_tile_blk<T, NW, DC>(tile, Q, p.ld, row0, len, colh + dc, w);
             __syncthreads();
-            float acc[AT_DCH];
-            weighted_rows_blk<NW, true>(dSm, tile, len, acc);
-            if (row < len) store_row<T>(dK + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
+            float acc[DC];
+            weighted_rows_blk<NW, true, DC>(dSm, tile, len, acc);
+            if (row < len) store_row_t<T, DC>(dK + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
         }
-        for (int dc = 0; dc < p.head_dim; dc += AT_DCH) {      // dV_j = sum_i P~_ij dO_i
-            const int w = min(AT_DCH, p.head_dim - dc);
+        for (int dc = 0; dc < p.head_dim; dc += DC) {      // dV_j = sum_i P~_ij dO_i
+            const int w = min(DC, p.head_dim - dc);
             __syncthreads();
-            load_tile_blk<T, NW>(tile, dO, p.ld_o, row0, len, colh + dc, w);
+            load_tile_blk<T, NW, DC>(tile, dO, p.ld_o, row0, len, colh + dc, w);
             __syncthreads();
-            float acc[AT_DCH];
-            weighted_rows_blk<NW, true>(Pm, tile, len, acc);
-            if (row < len) store_row<T>(dV + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
+            float acc[DC];
+            weighted_rows_blk<NW, true, DC>(Pm, tile, len, acc);
+            if (row < len) store_row_t<T, DC>(dV + (size_t)(row0 + row) * p.ld + colh + dc, acc, w);
         }
         __syncthreads();
     }
@@ -260,21 +297,21 @@ __global__ void __launch_bounds__(32 * NW) attn_gen_bwd_kernel(const GenAttnPara
     }
 }
 
-template <typename T, int NW>
+template <typename T, int NW, int DC>
 static int launch_gen(const GenAttnParams& p, bool bwd, cudaStream_t stream) {
     using G = GenCfg<NW>;
-    size_t smem = (size_t)(G::LMAX * AT_DCH + (bwd ? 2 : 1) * G::LMAX * G::LS) * sizeof(float);
+    size_t smem = (size_t)(G::LMAX * DC + (bwd ? 2 : 1) * G::LMAX * G::LS) * sizeof(float);
     if (bwd && p.dbias) smem += (size_t)p.seqlen * p.seqlen * sizeof(float);
     int gx = (num_sms() * (NW == 4 ? 2 : 4) + p.n_heads - 1) / p.n_heads;
     if (gx > p.n_seq) gx = p.n_seq;
     if (gx < 1) gx = 1;
     dim3 grid(gx, p.n_heads);
     if (!bwd) {
-        auto kern = attn_gen_fwd_kernel<T, NW>;
+        auto kern = attn_gen_fwd_kernel<T, NW, DC>;
         MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         kern<<<grid, 32 * NW, smem, stream>>>(p);
     } else {
-        auto kern = attn_gen_bwd_kernel<T, NW>;
+        auto kern = attn_gen_bwd_kernel<T, NW, DC>;
         MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         kern<<<grid, 32 * NW, smem, stream>>>(p);
     }
@@ -291,14 +328,18 @@ static int dispatch_gen(const GenAttnParams& p, bool bwd, int dtype, cudaStream_
     MOREC_CHECK_ARG(!(p.cu_seqlens && (p.bias || p.mask)), "attn_gen: bias / mask require fixed-length sequences");
     if (p.n_seq <= 0) return MOREC_OK;
     const int nw = (p.seqlen + 31) / 32;
+    const bool narrow = p.head_dim <= 32;         // Swin heads are 32 wide: half-width register slices / smem tile
+#define MOREC_GEN(TT, NWW)                                                                         \
+    return narrow ? launch_gen<TT, NWW, 32>(p, bwd, stream) : launch_gen<TT, NWW, 64>(p, bwd, stream)
     if (dtype == 1) {
-        if (nw <= 1) return launch_gen<__nv_bfloat16, 1>(p, bwd, stream);
-        if (nw == 2) return launch_gen<__nv_bfloat16, 2>(p, bwd, stream);
-        return launch_gen<__nv_bfloat16, 4>(p, bwd, stream);
+        if (nw <= 1) { MOREC_GEN(__nv_bfloat16, 1); }
+        if (nw == 2) { MOREC_GEN(__nv_bfloat16, 2); }
+        MOREC_GEN(__nv_bfloat16, 4);
     }
-    if (nw <= 1) return launch_gen<float, 1>(p, bwd, stream);
-    if (nw == 2) return launch_gen<float, 2>(p, bwd, stream);
-    return launch_gen<float, 4>(p, bwd, stream);
+    if (nw <= 1) { MOREC_GEN(float, 1); }
+    if (nw == 2) { MOREC_GEN(float, 2); }
+    MOREC_GEN(float, 4);
+#undef MOREC_GEN
 }
 
 }  // namespace morec
