@@ -12,6 +12,7 @@
 // batches (SASRec) by seqlen + an optional [n_seq, seqlen] key-valid mask and a causal flag.
 #include "../../../include/morec_b200.h"
 #include "attention_common.cuh"
+#include "attention_tc.cuh"
 
 namespace morec {
 
@@ -259,6 +260,16 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_kernel(const AttnParam
     }
 }
 
+// fast precision modes (dtype 0 / 1) with 32- or 64-wide heads run on the tensor-core kernels (attention_tc.cuh)
+static TcAttnParams tc_params(const AttnParams& p) {
+    TcAttnParams t{};
+    t.q = p.q; t.k = p.k; t.v = p.v; t.o = p.o; t.out = p.out; t.dq = p.dq; t.dk = p.dk; t.dv = p.dv;
+    t.cu_seqlens = p.cu_seqlens; t.key_mask = p.key_mask; t.causal = p.causal; t.masked_add = p.masked_add;
+    t.n_seq = p.n_seq; t.seqlen = p.seqlen; t.n_heads = p.n_heads; t.head_dim = p.head_dim; t.ld = p.ld; t.ld_o = p.ld_o;
+    t.scale = p.scale; t.dropout_p = p.dropout_p; t.seed = p.seed; t.offset = p.offset;
+    return t;
+}
+
 static int check(const AttnParams& p) {
     MOREC_CHECK_ARG(p.q && p.k && p.v, "attention: null q/k/v");
     MOREC_CHECK_ARG(p.head_dim % 4 == 0 && p.head_dim > 0, "attention: head_dim=%d must be a multiple of 4", p.head_dim);
@@ -283,6 +294,7 @@ extern "C" int morec_attn_fwd(const void* q, const void* k, const void* v, void*
     MOREC_CHECK_ARG(o, "attn_fwd: null output");
     if (int rc = check(p)) return rc;
     if (n_seq <= 0) return MOREC_OK;
+    if (tc_attn_eligible(dtype, seqlen, head_dim, ld, ld_o)) return tc_attn_dispatch(tc_params(p), false, dtype, (cudaStream_t)stream);
     const int pairs = n_seq * n_heads;
     int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
     const int cap = num_sms() * 16;
@@ -294,7 +306,7 @@ extern "C" int morec_attn_fwd(const void* q, const void* k, const void* v, void*
         MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    if (dtype == 0) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    if (dtype != 1) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     else attn_fwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
@@ -312,6 +324,7 @@ extern "C" int morec_attn_bwd(const void* q, const void* k, const void* v, const
     MOREC_CHECK_ARG(d_o && dq && dk && dv, "attn_bwd: null pointer");
     if (int rc = check(p)) return rc;
     if (n_seq <= 0) return MOREC_OK;
+    if (tc_attn_eligible(dtype, seqlen, head_dim, ld, ld_o)) return tc_attn_dispatch(tc_params(p), true, dtype, (cudaStream_t)stream);
     const int pairs = n_seq * n_heads;
     int blocks = (pairs + AT_WARPS - 1) / AT_WARPS;
     const int cap = num_sms() * 16;
@@ -323,7 +336,7 @@ extern "C" int morec_attn_bwd(const void* q, const void* k, const void* v, const
         MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    if (dtype == 0) attn_bwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    if (dtype != 1) attn_bwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     else attn_bwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;

@@ -12,6 +12,7 @@
 // all the sequences it visits and flushes it with one atomicAdd per entry.
 #include "../../../include/morec_b200.h"
 #include "attention_common.cuh"
+#include "attention_tc.cuh"
 
 namespace morec {
 
@@ -327,6 +328,14 @@ static int dispatch_gen(const GenAttnParams& p, bool bwd, int dtype, cudaStream_
     MOREC_CHECK_ARG(!p.mask || p.n_mask > 0, "attn_gen: mask needs n_mask > 0");
     MOREC_CHECK_ARG(!(p.cu_seqlens && (p.bias || p.mask)), "attn_gen: bias / mask require fixed-length sequences");
     if (p.n_seq <= 0) return MOREC_OK;
+    if (tc_attn_eligible(dtype, p.seqlen, p.head_dim, p.ld, p.ld_o)) {      // fast modes: tensor-core kernels
+        TcAttnParams t{};
+        t.q = p.q; t.k = p.k; t.v = p.v; t.o = p.o; t.out = p.out; t.dq = p.dq; t.dk = p.dk; t.dv = p.dv;
+        t.cu_seqlens = p.cu_seqlens; t.bias = p.bias; t.mask = p.mask; t.n_mask = p.n_mask; t.dbias = p.dbias;
+        t.n_seq = p.n_seq; t.seqlen = p.seqlen; t.n_heads = p.n_heads; t.head_dim = p.head_dim; t.ld = p.ld; t.ld_o = p.ld_o;
+        t.scale = p.scale; t.dropout_p = p.dropout_p; t.seed = p.seed; t.offset = p.offset;
+        return tc_attn_dispatch(t, bwd, dtype, stream);
+    }
     const int nw = (p.seqlen + 31) / 32;
     const bool narrow = p.head_dim <= 32;         // Swin heads are 32 wide: half-width register slices / smem tile
 #define MOREC_GEN(TT, NWW)                                                                         \

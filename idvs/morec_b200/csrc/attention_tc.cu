@@ -1,0 +1,22 @@
+// Dispatch of the tensor-core attention kernels (attention_tc.cuh) by storage type, head width and padded length.
+#include "../../../include/morec_b200.h"
+#include "attention_tc.cuh"
+
+namespace morec {
+
+template <typename T>
+static int tc_by_shape(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
+    const bool small = p.seqlen <= 32;
+    if (p.head_dim == 256) return tc_launch<T, 256, 32>(p, bwd, stream);
+    if (p.head_dim == 64) return small ? tc_launch<T, 64, 32>(p, bwd, stream) : tc_launch<T, 64, 64>(p, bwd, stream);
+    return small ? tc_launch<T, 32, 32>(p, bwd, stream) : tc_launch<T, 32, 64>(p, bwd, stream);
+}
+
+int tc_attn_dispatch(const TcAttnParams& p, bool bwd, int dtype, cudaStream_t stream) {
+    MOREC_CHECK_ARG(tc_attn_eligible(dtype, p.seqlen, p.head_dim, p.ld, p.ld_o), "attn_tc: unsupported shape");
+    MOREC_CHECK_ARG(!p.mask || p.n_mask > 0, "attn_tc: mask needs n_mask > 0");
+    if (p.n_seq <= 0) return MOREC_OK;
+    return dtype == 1 ? tc_by_shape<__nv_bfloat16>(p, bwd, stream) : tc_by_shape<float>(p, bwd, stream);
+}
+
+}  // namespace morec

@@ -29,11 +29,11 @@ extern "C" int morec_bert_layer_fwd(const MorecBertLayerFwd* a, void* stream) {
     const char* q = (const char*)a->qkv;
     if (a->max_len <= 32) {
         RUN(morec_attn_fwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->ctx, a->cu_seqlens, nullptr, 0, a->n_seq,
-                           a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, -1e9f, st, a->p_attn, a->seed,
+                           a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, -1e9f, a->dtype, a->p_attn, a->seed,
                            a->off_attn, stream));
     } else {   // long titles (cfg-2: T = 128): general kernel, one CTA per (sequence, head)
         RUN(morec_attn_gen_fwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->ctx, a->cu_seqlens, nullptr, nullptr, 0,
-                               a->n_seq, a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, st, a->p_attn,
+                               a->n_seq, a->max_len, a->n_heads, H / a->n_heads, 3 * H, H, scale, a->dtype, a->p_attn,
                                a->seed, a->off_attn, stream));
     }
     RUN(morec_gemm(a->ctx, a->w_ao, a->tmp_h, nullptr, a->b_ao, nullptr, M, H, H, H, H, H, 0, 0, 0, a->dtype, obf,
@@ -87,11 +87,11 @@ extern "C" int morec_bert_layer_bwd(const MorecBertLayerBwd* a, void* stream) {
     if (f->max_len <= 32) {
         RUN(morec_attn_bwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->dctx, dq, dq + (size_t)H * es,
                            dq + (size_t)2 * H * es, f->cu_seqlens, nullptr, 0, f->n_seq, f->max_len, f->n_heads,
-                           H / f->n_heads, 3 * H, H, scale, -1e9f, st, f->p_attn, f->seed, f->off_attn, stream));
+                           H / f->n_heads, 3 * H, H, scale, -1e9f, f->dtype, f->p_attn, f->seed, f->off_attn, stream));
     } else {
         RUN(morec_attn_gen_bwd(q, q + (size_t)H * es, q + (size_t)2 * H * es, a->dctx, dq, dq + (size_t)H * es,
                                dq + (size_t)2 * H * es, nullptr, f->cu_seqlens, nullptr, nullptr, 0, f->n_seq,
-                               f->max_len, f->n_heads, H / f->n_heads, 3 * H, H, scale, st, f->p_attn, f->seed,
+                               f->max_len, f->n_heads, H / f->n_heads, 3 * H, H, scale, f->dtype, f->p_attn, f->seed,
                                f->off_attn, stream));
     }
     // ---- fused QKV projection: dWqkv, dbqkv, dx (second part of the layer-input gradient; the first is dz1)

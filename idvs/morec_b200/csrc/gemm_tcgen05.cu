@@ -66,6 +66,7 @@ struct StdEpi {
         const void* aux;     // [M, ldaux] or null (dtype = aux_bf16 ? bf16 : fp32)
         int ldaux;
         int aux_bf16;
+        int fast;            // 1: polynomial erf (|err| <= 1.5e-7) in the GELU epilogues (fast modes); 0: erff (parity mode)
     };
 
     __device__ __forceinline__ static void load_aux(const Params& ep, float (&a)[32], int row, int col0, int M, int N) {
@@ -84,8 +85,22 @@ struct StdEpi {
                 }
             } else {
                 const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+                if (col0 + 32 <= N && (ep.ldaux & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0) {
+                    // 4 x 16-byte loads per row (the scalar form issued 32 two-byte loads, each touching 32 sectors)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __bfloat162float(ap[j]) : 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + j);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            a[8 * j + 2 * e] = __low2float(h[e]);
+                            a[8 * j + 2 * e + 1] = __high2float(h[e]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __bfloat162float(ap[j]) : 0.f;
+                }
             }
         } else {
 #pragma unroll
@@ -119,13 +134,23 @@ struct StdEpi {
             case MOREC_EPI_GELU: {
                 // pre-activation to C2 first (kept for the backward), then the activation to C
                 st.put(&tmC2, x, c, obf, 1, 2);
+                if (ep.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                }
                 break;
             }
             case MOREC_EPI_GELU_NOSAVE: {
+                if (ep.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+                }
                 break;
             }
             case MOREC_EPI_RELU: {
@@ -136,8 +161,13 @@ struct StdEpi {
             case MOREC_EPI_MUL_GELU_GRAD: {
                 float a[32];
                 load_aux(ep, a, row, col0, s.M, s.N);
+                if (ep.fast) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(a[j]);
+                    for (int j = 0; j < 32; ++j) x[j] *= gelu_fast_grad(a[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(a[j]);
+                }
                 break;
             }
             case MOREC_EPI_MUL_RELU_GRAD: {
@@ -209,5 +239,6 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
     StdEpi::Params ep;
     ep.mode = epilogue; ep.alpha = alpha; ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux;
     ep.aux_bf16 = (dtype == 1);
+    ep.fast = (dtype != 2);
     return gemm_dispatch_auto<StdEpi>(g, ep, (cudaStream_t)stream);
 }

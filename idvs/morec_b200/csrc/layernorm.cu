@@ -5,7 +5,7 @@
 // HBM-bound: forward reads x (+residual), writes y; backward reads dy (+dy2), y, writes dz (+dx_branch).
 // The backward reconstructs xhat from the saved output: xhat = (y - beta) / gamma  (gamma must be non-zero),
 // so neither the LN input nor the mean is kept.  Column reductions (dgamma, dbeta, dbias, dpos) are accumulated in
-// registers per CTA and flushed with one atomicAdd per column per CTA: the target buffers must be zero-initialised
+// registers per thread and flushed with one (vector) atomicAdd per column group per CTA: the target buffers must be zero-initialised
 // (or hold a gradient to accumulate into).
 #include "../../../include/morec_b200.h"
 #include "common.cuh"
@@ -124,100 +124,111 @@ struct LnBwdParams {
     float p_pre, p_post; uint64_t seed, off_pre, off_post;
 };
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
-    extern __shared__ float red[];   // [LN_WARPS][3][H] for the column reductions
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Backward: thread c owns float4 column c of EVERY row its CTA visits (blockDim = H/4 rounded up to a warp), so the
+// three column reductions cost 12 registers per thread instead of 3*H/32 per lane (the former warp-per-row layout
+// needed 230 registers at H = 768 and ran 8 warps per SM: 72 us against a 24 us HBM floor).  Rows are processed LN_R at
+// a time; their 2*LN_R row statistics are reduced with one warp shuffle tree each plus ONE __syncthreads per group
+// (partials double-buffered in shared memory).
+constexpr int LN_R = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(512) ln_bwd_kernel(const LnBwdParams p) {
+    __shared__ __align__(16) float red[2][16][2 * LN_R];
+    const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
+    const int nwarps = blockDim.x >> 5;
     const int nv = p.H >> 2;
+    const bool act = c < nv;
+    const float invH = 1.f / (float)p.H;
     const uint32_t th_pre = (uint32_t)fminf(p.p_pre * 4294967296.f, 4294967295.f);
     const uint32_t th_post = (uint32_t)fminf(p.p_post * 4294967296.f, 4294967295.f);
     const float sc_pre = p.p_pre > 0.f ? 1.f / (1.f - p.p_pre) : 1.f;
     const float sc_post = p.p_post > 0.f ? 1.f / (1.f - p.p_post) : 1.f;
-    float4 ag[NV], ab[NV], ax[NV];   // dgamma, dbeta, dbias partials
-    float4 gam[NV], bet[NV], igam[NV];   // this lane's columns of gamma, beta, 1/gamma (loop invariant)
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        ag[j] = ab[j] = ax[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int i = lane + 32 * j;
-        if (i < nv) {
-            gam[j] = *reinterpret_cast<const float4*>(p.gamma + 4 * i);
-            bet[j] = *reinterpret_cast<const float4*>(p.beta + 4 * i);
-            igam[j] = make_float4(1.f / gam[j].x, 1.f / gam[j].y, 1.f / gam[j].z, 1.f / gam[j].w);
-        } else {
-            gam[j] = bet[j] = igam[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, ax = ag;      // dgamma, dbeta, dbias partials of column c
+    float4 gam = ag, bet = ag, ig = ag;
+    if (act) {
+        gam = *reinterpret_cast<const float4*>(p.gamma + 4 * c);
+        bet = *reinterpret_cast<const float4*>(p.beta + 4 * c);
+        ig = make_float4(1.f / gam.x, 1.f / gam.y, 1.f / gam.z, 1.f / gam.w);
     }
-
-    for (int row = blockIdx.x * LN_WARPS + warp; row < p.M; row += gridDim.x * LN_WARPS) {
-        const T* dyr = reinterpret_cast<const T*>(p.dy) + (size_t)row * p.H;
-        const T* dy2r = p.dy2 ? reinterpret_cast<const T*>(p.dy2) + (size_t)row * p.H : nullptr;
-        const T* yr = reinterpret_cast<const T*>(p.y) + (size_t)row * p.H;
-        const float rstd = p.rstd[row];
-        float4 g[NV], xh[NV];
-        float s1 = 0.f, s2 = 0.f;
+    const T* dyb = reinterpret_cast<const T*>(p.dy);
+    const T* dy2b = reinterpret_cast<const T*>(p.dy2);
+    const T* yb = reinterpret_cast<const T*>(p.y);
+    T* dzb = reinterpret_cast<T*>(p.dz);
+    T* dxb = reinterpret_cast<T*>(p.dx_branch);
+    int buf = 0;
+    for (int row0 = blockIdx.x * LN_R; row0 < p.M; row0 += gridDim.x * LN_R, buf ^= 1) {
+        float4 d[LN_R], yv[LN_R];
+        float rs[LN_R];
+        // ---- all global loads of the row group first
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int i = lane + 32 * j;
-            if (i < nv) {
-                float4 d = load4<T>(dyr + 4 * i);
-                if (dy2r) { const float4 e = load4<T>(dy2r + 4 * i); d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w; }
-                if (p.p_post > 0.f) d = drop4(d, p.seed, p.off_post + (uint64_t)row * nv + i, th_post, sc_post);
-                const float4 yv = load4<T>(yr + 4 * i);
-                const float4 ga = gam[j], be = bet[j], ig = igam[j];
-                float4 h;
-                h.x = (yv.x - be.x) * ig.x; h.y = (yv.y - be.y) * ig.y; h.z = (yv.z - be.z) * ig.z; h.w = (yv.w - be.w) * ig.w;
-                ag[j].x += d.x * h.x; ag[j].y += d.y * h.y; ag[j].z += d.z * h.z; ag[j].w += d.w * h.w;
-                ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
-                d.x *= ga.x; d.y *= ga.y; d.z *= ga.z; d.w *= ga.w;
-                g[j] = d; xh[j] = h;
-                s1 += d.x + d.y + d.z + d.w;
-                s2 += d.x * h.x + d.y * h.y + d.z * h.z + d.w * h.w;
+        for (int r = 0; r < LN_R; ++r) {
+            const int row = row0 + r;
+            d[r] = yv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rs[r] = 0.f;
+            if (act && row < p.M) {
+                const size_t o = (size_t)row * p.H + 4 * c;
+                d[r] = load4<T>(dyb + o);
+                if (dy2b) { const float4 e = load4<T>(dy2b + o); d[r].x += e.x; d[r].y += e.y; d[r].z += e.z; d[r].w += e.w; }
+                yv[r] = load4<T>(yb + o);
+                rs[r] = p.rstd[row];
             }
         }
-        const float m1 = warp_sum(s1) / p.H, m2 = warp_sum(s2) / p.H;
-        T* dzr = reinterpret_cast<T*>(p.dz) + (size_t)row * p.H;
-        T* dxr = p.dx_branch ? reinterpret_cast<T*>(p.dx_branch) + (size_t)row * p.H : nullptr;
-        float* dpr = p.dpos ? p.dpos + (size_t)(row % p.pos_period) * p.H : nullptr;
+        float st[2 * LN_R];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int i = lane + 32 * j;
-            if (i < nv) {
-                float4 o;
-                o.x = rstd * (g[j].x - m1 - xh[j].x * m2);
-                o.y = rstd * (g[j].y - m1 - xh[j].y * m2);
-                o.z = rstd * (g[j].z - m1 - xh[j].z * m2);
-                o.w = rstd * (g[j].w - m1 - xh[j].w * m2);
-                store4<T>(dzr + 4 * i, o);
-                if (dpr) {
-                    atomicAdd(dpr + 4 * i, o.x); atomicAdd(dpr + 4 * i + 1, o.y);
-                    atomicAdd(dpr + 4 * i + 2, o.z); atomicAdd(dpr + 4 * i + 3, o.w);
-                }
-                float4 b = o;
-                if (p.p_pre > 0.f) b = drop4(o, p.seed, p.off_pre + (uint64_t)row * nv + i, th_pre, sc_pre);
-                if (dxr) store4<T>(dxr + 4 * i, b);
-                ax[j].x += b.x; ax[j].y += b.y; ax[j].z += b.z; ax[j].w += b.w;
+        for (int r = 0; r < LN_R; ++r) {
+            const int row = row0 + r;
+            float4 dd = d[r], h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act && row < p.M) {
+                if (p.p_post > 0.f) dd = drop4(dd, p.seed, p.off_post + (uint64_t)row * nv + c, th_post, sc_post);
+                h.x = (yv[r].x - bet.x) * ig.x; h.y = (yv[r].y - bet.y) * ig.y;
+                h.z = (yv[r].z - bet.z) * ig.z; h.w = (yv[r].w - bet.w) * ig.w;
+                ag.x += dd.x * h.x; ag.y += dd.y * h.y; ag.z += dd.z * h.z; ag.w += dd.w * h.w;
+                ab.x += dd.x; ab.y += dd.y; ab.z += dd.z; ab.w += dd.w;
+                dd.x *= gam.x; dd.y *= gam.y; dd.z *= gam.z; dd.w *= gam.w;
+            }
+            d[r] = dd; yv[r] = h;                       // d <- dy*gamma, yv <- xhat
+            st[2 * r] = warp_sum(dd.x + dd.y + dd.z + dd.w);
+            st[2 * r + 1] = warp_sum(dd.x * h.x + dd.y * h.y + dd.z * h.z + dd.w * h.w);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 2 * LN_R; i += 4)
+                *reinterpret_cast<float4*>(&red[buf][warp][i]) = make_float4(st[i], st[i + 1], st[i + 2], st[i + 3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2 * LN_R; ++i) st[i] = 0.f;
+        for (int w = 0; w < nwarps; ++w) {
+#pragma unroll
+            for (int i = 0; i < 2 * LN_R; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&red[buf][w][i]);
+                st[i] += v.x; st[i + 1] += v.y; st[i + 2] += v.z; st[i + 3] += v.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < LN_R; ++r) {
+            const int row = row0 + r;
+            if (act && row < p.M) {
+                const float m1 = st[2 * r] * invH, m2 = st[2 * r + 1] * invH, rstd = rs[r];
+                const size_t o = (size_t)row * p.H + 4 * c;
+                float4 z;
+                z.x = rstd * (d[r].x - m1 - yv[r].x * m2);
+                z.y = rstd * (d[r].y - m1 - yv[r].y * m2);
+                z.z = rstd * (d[r].z - m1 - yv[r].z * m2);
+                z.w = rstd * (d[r].w - m1 - yv[r].w * m2);
+                store4<T>(dzb + o, z);
+                if (p.dpos) atomicAdd(reinterpret_cast<float4*>(p.dpos + (size_t)(row % p.pos_period) * p.H + 4 * c), z);
+                float4 b = z;
+                if (p.p_pre > 0.f) b = drop4(z, p.seed, p.off_pre + (uint64_t)row * nv + c, th_pre, sc_pre);
+                if (dxb) store4<T>(dxb + o, b);
+                ax.x += b.x; ax.y += b.y; ax.z += b.z; ax.w += b.w;
             }
         }
     }
-    // ---- column reductions: warps -> smem -> one atomicAdd per column per CTA
-    float* rg = red + (size_t)warp * 3 * p.H;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nv) {
-            *reinterpret_cast<float4*>(rg + 4 * i) = ag[j];
-            *reinterpret_cast<float4*>(rg + p.H + 4 * i) = ab[j];
-            *reinterpret_cast<float4*>(rg + 2 * p.H + 4 * i) = ax[j];
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < 3 * p.H; c += blockDim.x) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) s += red[(size_t)w * 3 * p.H + c];
-        const int which = c / p.H, col = c % p.H;
-        float* dst = which == 0 ? p.dgamma : which == 1 ? p.dbeta : p.dbias;
-        if (dst) atomicAdd(dst + col, s);
+    if (act) {          // one vector atomic per column group per CTA
+        if (p.dgamma) atomicAdd(reinterpret_cast<float4*>(p.dgamma + 4 * c), ag);
+        if (p.dbeta) atomicAdd(reinterpret_cast<float4*>(p.dbeta + 4 * c), ab);
+        if (p.dbias) atomicAdd(reinterpret_cast<float4*>(p.dbias + 4 * c), ax);
     }
 }
 
@@ -262,29 +273,12 @@ extern "C" int morec_layernorm_bwd(const void* dy, const void* dy2, const void* 
     if (M <= 0) return MOREC_OK;
     LnBwdParams p{dy, dy2, y, gamma, beta, rstd, dz, dx_branch, dgamma, dbeta, dbias, dpos,
                   pos_period > 0 ? pos_period : 1, M, H, p_pre, p_post, seed, off_pre, off_post};
-    int blocks = (M + LN_WARPS - 1) / LN_WARPS;
-    const int cap = num_sms() * 2;
+    const int threads = ((H / 4 + 31) / 32) * 32;                 // <= 512
+    int blocks = (M + LN_R - 1) / LN_R;
+    const int cap = num_sms() * (threads <= 64 ? 16 : threads <= 128 ? 8 : threads <= 256 ? 4 : 2);
     if (blocks > cap) blocks = cap;
-    const size_t smem = (size_t)LN_WARPS * 3 * H * sizeof(float);
-    const int nvl = (H / 4 + 31) / 32;
-#define LN_BWD(TT, NVV)                                                                                              \
-    do {                                                                                                             \
-        static bool set_ = false;                                                                                    \
-        if (!set_) {                                                                                                 \
-            MOREC_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<TT, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                            200 * 1024));                                                            \
-            set_ = true;                                                                                             \
-        }                                                                                                            \
-        ln_bwd_kernel<TT, NVV><<<blocks, LN_WARPS * 32, smem, (cudaStream_t)stream>>>(p);                            \
-    } while (0)
-#define LN_BWD_T(NVV)                                         \
-    do {                                                      \
-        if (dtype == 0) LN_BWD(float, NVV);                   \
-        else LN_BWD(__nv_bfloat16, NVV);                      \
-    } while (0)
-    if (nvl <= 2) LN_BWD_T(2); else if (nvl <= 4) LN_BWD_T(4); else if (nvl <= 6) LN_BWD_T(6); else if (nvl <= 8) LN_BWD_T(8); else LN_BWD_T(16);
-#undef LN_BWD_T
-#undef LN_BWD
+    if (dtype == 1) ln_bwd_kernel<__nv_bfloat16><<<blocks, threads, 0, (cudaStream_t)stream>>>(p);
+    else ln_bwd_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(p);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

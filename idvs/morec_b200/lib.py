@@ -343,7 +343,7 @@ def attn_fwd(q, k, v, o, *, cu_seqlens=None, key_mask=None, causal=False, n_seq,
     assert q.stride(0) == k.stride(0) == v.stride(0)
     rc = load().morec_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(key_mask), int(causal),
                                n_seq, seqlen, n_heads, head_dim, q.stride(0),
-                               o.stride(0), scale, masked_add, dtype_code(q), dropout_p, _u64(seed),
+                               o.stride(0), scale, masked_add, gemm_dtype_code(q), dropout_p, _u64(seed),
                                _u64(offset), _stream())
     _check(rc, "morec_attn_fwd")
     return o
@@ -355,7 +355,7 @@ def attn_bwd(q, k, v, do, dq, dk, dv, *, cu_seqlens=None, key_mask=None, causal=
     rc = load().morec_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(cu_seqlens),
                                _ptr(key_mask), int(causal), n_seq, seqlen, n_heads,
                                head_dim, q.stride(0), do.stride(0), scale, masked_add,
-                               dtype_code(q), dropout_p, _u64(seed), _u64(offset), _stream())
+                               gemm_dtype_code(q), dropout_p, _u64(seed), _u64(offset), _stream())
     _check(rc, "morec_attn_bwd")
 
 
@@ -364,7 +364,7 @@ def attn_gen_fwd(q, k, v, o, *, cu_seqlens=None, bias=None, mask=None, n_seq, se
     assert q.stride(0) == k.stride(0) == v.stride(0)
     rc = load().morec_attn_gen_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(cu_seqlens), _ptr(bias), _ptr(mask),
                                    (mask.shape[0] if mask is not None else 0), n_seq, seqlen, n_heads, head_dim,
-                                   q.stride(0), o.stride(0), scale, dtype_code(q), dropout_p, _u64(seed), _u64(offset),
+                                   q.stride(0), o.stride(0), scale, gemm_dtype_code(q), dropout_p, _u64(seed), _u64(offset),
                                    _stream())
     _check(rc, "morec_attn_gen_fwd")
     return o
@@ -375,7 +375,7 @@ def attn_gen_bwd(q, k, v, do, dq, dk, dv, *, dbias=None, cu_seqlens=None, bias=N
     assert q.stride(0) == k.stride(0) == v.stride(0) == dq.stride(0) == dk.stride(0) == dv.stride(0)
     rc = load().morec_attn_gen_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dbias),
                                    _ptr(cu_seqlens), _ptr(bias), _ptr(mask), (mask.shape[0] if mask is not None else 0),
-                                   n_seq, seqlen, n_heads, head_dim, q.stride(0), do.stride(0), scale, dtype_code(q),
+                                   n_seq, seqlen, n_heads, head_dim, q.stride(0), do.stride(0), scale, gemm_dtype_code(q),
                                    dropout_p, _u64(seed), _u64(offset), _stream())
     _check(rc, "morec_attn_gen_bwd")
 

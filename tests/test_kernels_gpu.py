@@ -419,3 +419,160 @@ def test_scale_add_and_mean_rows(lib):
     ref = x + gs.repeat_interleave(rpg).view(-1, 1) * y[perm.long()]
     assert torch.allclose(out, ref, atol=1e-6)
     assert torch.allclose(lib.mean_rows(x, 2, rpg), x.view(2, rpg, H).mean(1), atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core attention (attention_tc.cuh): the fast modes ("tf32": fp32 storage under fp32_mode(False); "bf16")
+# route 32/64-wide heads with <= 64 tokens to mma.sync TF32 kernels.  Tolerances are TF32-grade (2^-11 operand
+# rounding), written per test.
+# ---------------------------------------------------------------------------------------------------------------
+def _tc_modes():
+    return [(torch.float32, 3e-3, 6e-3), (torch.bfloat16, 1.2e-2, 2e-2)]
+
+
+@pytest.mark.parametrize("dt,tol_f,tol_b", _tc_modes())
+@pytest.mark.parametrize("n_heads,dh,L", [(12, 64, 30), (4, 32, 25), (2, 64, 8), (3, 64, 32), (2, 32, 17), (2, 256, 25), (2, 256, 32)])
+def test_attention_tc_fixed_causal_keymask(lib, dt, tol_f, tol_b, n_heads, dh, L):
+    torch.manual_seed(dh + L)
+    B, H = 7, n_heads * dh
+    qkv = (torch.randn(B * L, 3 * H, device="cuda") * 0.5).to(dt)
+    lm = (torch.rand(B, L, device="cuda") > 0.3).float()
+    lm[:, -1] = 1
+    lm[0] = 0
+    lm[0, -1] = 1
+    scale = 1 / math.sqrt(dh)
+    o = torch.full((B * L, H), float("nan"), device="cuda", dtype=dt)
+    with lib.fp32_mode(False):
+        lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, key_mask=lm, causal=True, n_seq=B, seqlen=L,
+                     n_heads=n_heads, head_dim=dh, scale=scale)
+    qd = qkv.double().requires_grad_(True)
+    ok = torch.tril(torch.ones(L, L, device="cuda", dtype=torch.bool)).view(1, 1, L, L) & (lm != 0).view(B, 1, 1, L)
+    add = torch.where(ok, 0.0, -1e9).double()
+    ref = _ref_attn(qd[:, :H].reshape(B, L, H), qd[:, H:2 * H].reshape(B, L, H), qd[:, 2 * H:].reshape(B, L, H), n_heads,
+                    scale, add).reshape(B * L, H)
+    assert rel(o, ref) < tol_f
+    do = torch.randn(B * L, H, device="cuda").to(dt)
+    ref.backward(do.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    with lib.fp32_mode(False):
+        lib.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+                     key_mask=lm, causal=True, n_seq=B, seqlen=L, n_heads=n_heads, head_dim=dh, scale=scale)
+    assert rel(dqkv, qd.grad) < tol_b
+
+
+@pytest.mark.parametrize("dt,tol_f,tol_b", _tc_modes())
+@pytest.mark.parametrize("dh,T,gen", [(64, 30, False), (64, 32, False), (32, 64, True), (64, 49, True)])
+def test_attention_tc_packed_varlen(lib, dt, tol_f, tol_b, dh, T, gen):
+    torch.manual_seed(5 + T)
+    n_heads = 4
+    H = n_heads * dh
+    lens = torch.tensor([T, 6, 17, 1, T - 1, 12, 16, 8, 9, min(T, 33)])
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    n_tok = int(cu[-1])
+    qkv = torch.randn(n_tok, 3 * H, device="cuda").to(dt)
+    o = torch.full((n_tok, H), float("nan"), device="cuda", dtype=dt)
+    cu_d = cu.cuda()
+    scale = 1 / math.sqrt(dh)
+    fwd, bwd = (lib.attn_gen_fwd, lib.attn_gen_bwd) if gen else (lib.attn_fwd, lib.attn_bwd)
+    do = torch.randn(n_tok, H, device="cuda").to(dt)
+    dqkv = torch.full_like(qkv, float("nan"))
+    with lib.fp32_mode(False):
+        fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, cu_seqlens=cu_d, n_seq=len(lens), seqlen=T, n_heads=n_heads,
+            head_dim=dh, scale=scale)
+        bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+            cu_seqlens=cu_d, n_seq=len(lens), seqlen=T, n_heads=n_heads, head_dim=dh, scale=scale)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(dqkv.float()).all()
+    for s in range(len(lens)):
+        a, b = int(cu[s]), int(cu[s + 1])
+        x = qkv[a:b].double().requires_grad_(True)
+        n = b - a
+        ref = _ref_attn(x[:, :H].reshape(1, n, H), x[:, H:2 * H].reshape(1, n, H), x[:, 2 * H:].reshape(1, n, H), n_heads, scale,
+                        torch.zeros(1, 1, n, n, device="cuda", dtype=torch.double)).reshape(n, H)
+        assert rel(o[a:b], ref) < tol_f, (s, n)
+        ref.backward(do[a:b].double())
+        assert rel(dqkv[a:b], x.grad) < tol_b, (s, n)
+
+
+@pytest.mark.parametrize("dt,tol_f,tol_b", _tc_modes())
+@pytest.mark.parametrize("n_heads,dh,L,bias,n_mask", [(3, 32, 49, True, 4), (12, 32, 49, True, 0), (2, 64, 40, False, 0), (6, 32, 49, True, 5)])
+def test_attention_tc_general_bias_mask(lib, dt, tol_f, tol_b, n_heads, dh, L, bias, n_mask):
+    """Swin windows (49 tokens, 32-wide heads, relative-position bias, shift mask, bias gradient) on the tensor-core path"""
+    torch.manual_seed(L + dh + n_heads)
+    nW, H = 13, n_heads * dh
+    qkv = (torch.randn(nW * L, 3 * H, device="cuda") * 0.5).to(dt)
+    B = (torch.randn(n_heads, L, L, device="cuda") * 0.3) if bias else None
+    Mk = None
+    if n_mask:
+        Mk = torch.where(torch.rand(n_mask, L, L, device="cuda") > 0.7, -100.0, 0.0)
+        Mk[:, torch.arange(L), torch.arange(L)] = 0.0
+    scale = 1 / math.sqrt(dh)
+    o = torch.full((nW * L, H), float("nan"), device="cuda", dtype=dt)
+    with lib.fp32_mode(False):
+        lib.attn_gen_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, bias=B, mask=Mk, n_seq=nW, seqlen=L,
+                         n_heads=n_heads, head_dim=dh, scale=scale)
+    qd = qkv.double().requires_grad_(True)
+    Bd = B.double().requires_grad_(True) if bias else None
+    add = torch.zeros(nW, n_heads, L, L, device="cuda", dtype=torch.double)
+    if bias:
+        add = add + Bd.unsqueeze(0)
+    if n_mask:
+        add = add + Mk.double()[torch.arange(nW, device="cuda") % n_mask].unsqueeze(1)
+    q = qd[:, :H].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    k = qd[:, H:2 * H].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    v = qd[:, 2 * H:].reshape(nW, L, n_heads, dh).transpose(1, 2)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * scale + add, -1) @ v).transpose(1, 2).reshape(nW * L, H)
+    assert rel(o, ref) < tol_f
+    do = torch.randn(nW * L, H, device="cuda").to(dt)
+    ref.backward(do.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    dB = torch.zeros(n_heads, L, L, device="cuda") if bias else None
+    with lib.fp32_mode(False):
+        lib.attn_gen_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:],
+                         dbias=dB, bias=B, mask=Mk, n_seq=nW, seqlen=L, n_heads=n_heads, head_dim=dh, scale=scale)
+    assert rel(dqkv, qd.grad) < tol_b
+    if bias:
+        assert rel(dB, Bd.grad) < tol_b
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dh,L", [(64, 30), (32, 25), (64, 49)])
+def test_attention_tc_dropout_mask_and_grads(lib, dt, dh, L):
+    """With V = [I | 0] the forward output IS the dropped, rescaled probability matrix, so the keep mask can be read
+    off; the backward must then equal autograd through softmax * mask / (1 - p) with that mask."""
+    torch.manual_seed(60 + L)
+    n_heads, B, p = 2, 9, 0.25
+    H = n_heads * dh
+    assert L <= dh
+    gen = L > 32
+    fwd, bwd = (lib.attn_gen_fwd, lib.attn_gen_bwd) if gen else (lib.attn_fwd, lib.attn_bwd)
+    qkv = torch.randn(B * L, 3 * H, device="cuda")
+    eye = torch.zeros(L, dh, device="cuda")
+    eye[torch.arange(L), torch.arange(L)] = 1.0
+    qkv[:, 2 * H:] = eye.repeat(B, n_heads)
+    qkv = qkv.to(dt)
+    kw = dict(n_seq=B, seqlen=L, n_heads=n_heads, head_dim=dh, scale=1 / math.sqrt(dh), dropout_p=p, seed=77, offset=5 << 36)
+    o1 = torch.empty(B * L, H, device="cuda", dtype=dt)
+    o2 = torch.empty_like(o1)
+    with lib.fp32_mode(False):
+        fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o1, **kw)
+        fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o2, **kw)
+    assert torch.equal(o1, o2)
+    Pd = o1.float().view(B, L, n_heads, dh)[..., :L].permute(0, 2, 1, 3)          # [B, heads, L(query), L(key)]
+    keep = (Pd != 0)
+    frac = float(keep.float().mean())
+    assert abs(frac - (1 - p)) < 0.02, frac
+    qd = qkv.double().requires_grad_(True)
+    q = qd[:, :H].reshape(B, L, n_heads, dh).transpose(1, 2)
+    k = qd[:, H:2 * H].reshape(B, L, n_heads, dh).transpose(1, 2)
+    v = qd[:, 2 * H:].reshape(B, L, n_heads, dh).transpose(1, 2)
+    P = torch.softmax(q @ k.transpose(-1, -2) * kw["scale"], -1) * keep.double() / (1 - p)
+    tol = 3e-3 if dt == torch.float32 else 1.2e-2
+    assert rel(Pd, P) < tol
+    ref = (P @ v).transpose(1, 2).reshape(B * L, H)
+    do = torch.randn(B * L, H, device="cuda").to(dt)
+    ref.backward(do.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    with lib.fp32_mode(False):
+        bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], **kw)
+    assert rel(dqkv, qd.grad) < 2 * tol
