@@ -10,7 +10,7 @@
 //                                   bytes, and both CTAs' TMA loads complete_tx on the leader's barrier (peer bit masked)
 //   empty[s]  (per CTA)            count 1: tcgen05.commit multicast from the leader frees the slot in both CTAs
 //   tfull[a]  (per CTA)            count 1: tcgen05.commit multicast when the accumulator stage is complete
-//   tempty[a] (leader's is used)   count 2*4: every epilogue warp of BOTH CTAs arrives (remote arrive from the peer)
+//   tempty[a] (leader's is used)   count 2*4*groups: every epilogue warp of BOTH CTAs arrives (remote arrive from the peer)
 #pragma once
 #include <stdlib.h>
 
@@ -86,8 +86,8 @@ struct Cfg2 {
     static constexpr int A_BYTES = BLOCK_M * 128;
     static constexpr int B_BYTES = HALF_N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // per CTA
-    static constexpr int EPI_BUFS = kEpiBufsPerWarp;
-    static constexpr int EPI_BYTES = kEpiWarps * EPI_BUFS * kEpiBufBytes;
+    static constexpr int EPI_SUBS = 16;                 // 4 KB staging sub-buffers per CTA, shared out over the epilogue warps
+    static constexpr int EPI_BYTES = EPI_SUBS * kEpiBufBytes;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (227 * 1024 - EPI_BYTES - BAR_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -95,8 +95,15 @@ struct Cfg2 {
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
 };
 
+// Epilogue warp groups: Epi::kGroups == 2 adds warps 8-11 as a second epilogue group (same TMEM lane quarters, the
+// other half of the tile's columns).  One warp per scheduler could not keep up with math-heavy epilogues: the GELU
+// forward / GELU-gradient epilogues (~25 instructions per element, dependent chains) paced the kernel at 143 us against
+// 50 us for the same GEMM with a plain epilogue.
+template <class Epi>
+constexpr int gemm2_threads() { return kThreads + (Epi::kGroups == 2 ? 128 : 0); }
+
 template <int KIND, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<Epi>(), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TileSched p,
              const typename Epi::Params ep) {
@@ -130,7 +137,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), 2 * kEpiWarps);
+            mbar_init(smem_u32(&tempty_bar[s]), 2 * kEpiWarps * Epi::kGroups);
         }
         mbar_fence_init();
     }
@@ -227,25 +234,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 4 + 4 * Epi::kGroups) {
         // ================================ epilogue (both CTAs, own 128 rows) ================================
-        const int q = warp - 4;
+        const int q = warp & 3;                    // TMEM lane quarter == warp % 4
+        const int cg = (warp - 4) >> 2;            // column group of this warp
+        constexpr int NSUB = C::EPI_SUBS / (4 * Epi::kGroups);
         EpiStore st;
-        st.bufs = epi_base + q * (C::EPI_BUFS * kEpiBufBytes);
-        st.nsub = C::EPI_BUFS;
+        st.bufs = epi_base + (cg * 4 + q) * (NSUB * kEpiBufBytes);
+        st.nsub = NSUB;
+        st.grp = 0;
         st.c_end = 0;
         st.lane = lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (pair < total_work) {                            // epilogue side inputs of the first tile -> L2
+            const int tile = pair / p.splits;
+            Epi::template prefetch<C::BLOCK_N>(ep, (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
+                                               (tile % p.n_tiles) * C::BLOCK_N, p);
+        }
         for (int w = pair; w < total_work; w += n_pairs) {
             const int split = w % p.splits;
             const int tile = w / p.splits;
             const int m0 = (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * C::BLOCK_N;
+            if (w + n_pairs < total_work) {                 // ... and of the next tile, one tile time ahead
+                const int nt = (w + n_pairs) / p.splits;
+                Epi::template prefetch<C::BLOCK_N>(ep, (nt / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
+                                                   (nt % p.n_tiles) * C::BLOCK_N, p);
+            }
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
-            Epi::template tile<C::BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::BLOCK_N, st, m0, q,
-                                           n0, split, p);
+            Epi::template tile<KIND, C::BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::BLOCK_N, st, m0, q,
+                                                 n0, split, p, cg, Epi::kGroups);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);    // leader's barrier
@@ -318,7 +338,7 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
         MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<2 * pairs, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
+    kern<<<2 * pairs, gemm2_threads<Epi>(), C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

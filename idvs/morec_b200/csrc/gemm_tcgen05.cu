@@ -1,9 +1,8 @@
-// Standard epilogue family of the tcgen05 GEMM + the C-ABI entry point morec_gemm (see include/morec_b200.h).
-#include "gemm2_tcgen05.cuh"
+// TMA descriptor construction + the C-ABI entry point morec_gemm (see include/morec_b200.h); the kernels live in
+// gemm_std_m<MODE>.cu, one translation unit per epilogue mode.
+#include "gemm_std_epi.cuh"
 
 #include <mutex>
-
-#include "../../../include/morec_b200.h"
 
 namespace morec {
 
@@ -55,164 +54,6 @@ int make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inne
     return MOREC_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// standard epilogues
-// ------------------------------------------------------------------------------------------------
-struct StdEpi {
-    struct Params {
-        int mode;
-        float alpha;
-        const float* bias;   // [N] fp32 or null
-        const void* aux;     // [M, ldaux] or null (dtype = aux_bf16 ? bf16 : fp32)
-        int ldaux;
-        int aux_bf16;
-        int fast;            // 1: polynomial erf (|err| <= 1.5e-7) in the GELU epilogues (fast modes); 0: erff (parity mode)
-    };
-
-    __device__ __forceinline__ static void load_aux(const Params& ep, float (&a)[32], int row, int col0, int M, int N) {
-        if (row < M) {
-            if (!ep.aux_bf16) {
-                const float* ap = reinterpret_cast<const float*>(ep.aux) + (size_t)row * ep.ldaux + col0;
-                if (col0 + 32 <= N) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + j);
-                        a[4 * j] = t.x; a[4 * j + 1] = t.y; a[4 * j + 2] = t.z; a[4 * j + 3] = t.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __ldg(ap + j) : 0.f;
-                }
-            } else {
-                const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
-                if (col0 + 32 <= N && (ep.ldaux & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0) {
-                    // 4 x 16-byte loads per row (the scalar form issued 32 two-byte loads, each touching 32 sectors)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + j);
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            a[8 * j + 2 * e] = __low2float(h[e]);
-                            a[8 * j + 2 * e + 1] = __high2float(h[e]);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __bfloat162float(ap[j]) : 0.f;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = 0.f;
-        }
-    }
-
-    __device__ __forceinline__ static void chunk(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
-                                                 EpiStore& st, const uint32_t (&v)[32], int c, int row, int row0,
-                                                 int n0, bool add_bias, const TileSched& s) {
-        const int col0 = n0 + c * 32;
-        const bool obf = s.out_bf16 != 0;
-        const int ns = ep.mode == MOREC_EPI_GELU ? 2 : 1;
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha;
-        if (add_bias) {
-            if (col0 + 32 <= s.N) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
-                    x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < s.N) x[j] += __ldg(ep.bias + col0 + j);
-            }
-        }
-        switch (ep.mode) {
-            case MOREC_EPI_GELU: {
-                // pre-activation to C2 first (kept for the backward), then the activation to C
-                st.put(&tmC2, x, c, obf, 1, 2);
-                if (ep.fast) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-                }
-                break;
-            }
-            case MOREC_EPI_GELU_NOSAVE: {
-                if (ep.fast) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_fast(x[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
-                }
-                break;
-            }
-            case MOREC_EPI_RELU: {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                break;
-            }
-            case MOREC_EPI_MUL_GELU_GRAD: {
-                float a[32];
-                load_aux(ep, a, row, col0, s.M, s.N);
-                if (ep.fast) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] *= gelu_fast_grad(a[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] *= gelu_erf_grad(a[j]);
-                }
-                break;
-            }
-            case MOREC_EPI_MUL_RELU_GRAD: {
-                float a[32];
-                load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
-                break;
-            }
-            default:
-                break;
-        }
-        st.put(&tmC, x, c, obf, 0, ns);
-        st.end_chunk(c, n0, row0, obf, s.accumulate != 0, ns);
-    }
-
-    template <int BLOCK_N>
-    __device__ __forceinline__ static void tile(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
-                                                uint32_t taddr, EpiStore& st, int m0, int q, int n0, int split,
-                                                const TileSched& s) {
-        const int row0 = m0 + q * 32;
-        if (row0 >= s.M) return;   // warp-uniform
-        const int row = row0 + st.lane;
-        int c_end = (s.N - n0 + 31) / 32;
-        if (c_end > BLOCK_N / 32) c_end = BLOCK_N / 32;
-        if (s.out_bf16) c_end = (c_end + 1) & ~1;
-        st.c_end = c_end;
-        const bool add_bias = ep.bias != nullptr && split == 0;
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is processed
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-#pragma unroll 1
-        for (int c = 0; c < c_end; c += 2) {
-            tc_wait_ld();
-            if (c + 1 < c_end) tmem_ld32(taddr + (c + 1) * 32, vb);
-            chunk(ep, tmC, tmC2, st, va, c, row, row0, n0, add_bias, s);
-            if (c + 1 < c_end) {
-                tc_wait_ld();
-                if (c + 2 < c_end) tmem_ld32(taddr + (c + 2) * 32, va);
-                chunk(ep, tmC, tmC2, st, vb, c + 1, row, row0, n0, add_bias, s);
-            }
-        }
-    }
-};
-
 }  // namespace morec
 
 // ------------------------------------------------------------------------------------------------
@@ -236,9 +77,16 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
     g.a_mn = a_mn_major; g.b_mn = b_mn_major;
     g.dtype = dtype; g.out_bf16 = out_bf16;
     g.accumulate = accumulate; g.allow_split_k = accumulate;
-    StdEpi::Params ep;
+    StdEpiParams ep;
     ep.mode = epilogue; ep.alpha = alpha; ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux;
     ep.aux_bf16 = (dtype == 1);
-    ep.fast = (dtype != 2);
-    return gemm_dispatch_auto<StdEpi>(g, ep, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (epilogue) {
+        case MOREC_EPI_LINEAR: return gemm_std_run_0(g, ep, st);
+        case MOREC_EPI_GELU: return gemm_std_run_1(g, ep, st);
+        case MOREC_EPI_GELU_NOSAVE: return gemm_std_run_2(g, ep, st);
+        case MOREC_EPI_RELU: return gemm_std_run_3(g, ep, st);
+        case MOREC_EPI_MUL_GELU_GRAD: return gemm_std_run_4(g, ep, st);
+        default: return gemm_std_run_5(g, ep, st);
+    }
 }

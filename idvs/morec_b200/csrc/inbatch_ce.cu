@@ -64,9 +64,12 @@ struct CeParams {
 
 struct CeFwdEpi {
     using Params = CeParams;
+    static constexpr int kGroups = 1;      // row statistics span the whole tile: one warp per row quarter
     template <int BLOCK_N>
+    __device__ __forceinline__ static void prefetch(const Params&, int, int, const TileSched&) {}
+    template <int KIND, int BLOCK_N>
     __device__ __forceinline__ static void tile(const Params& ep, const CUtensorMap&, const CUtensorMap&, uint32_t taddr,
-                                                EpiStore& st, int m0, int q, int n0, int, const TileSched& s) {
+                                                EpiStore& st, int m0, int q, int n0, int, const TileSched& s, int, int) {
         const int row0 = m0 + q * 32;
         if (row0 >= s.M) return;
         const int row = row0 + st.lane;
@@ -114,10 +117,13 @@ struct CeFwdEpi {
 
 struct CeBwdEpi {
     using Params = CeParams;
+    static constexpr int kGroups = 1;
     template <int BLOCK_N>
+    __device__ __forceinline__ static void prefetch(const Params&, int, int, const TileSched&) {}
+    template <int KIND, int BLOCK_N>
     __device__ __forceinline__ static void tile(const Params& ep, const CUtensorMap& tmC, const CUtensorMap&,
                                                 uint32_t taddr, EpiStore& st, int m0, int q, int n0, int,
-                                                const TileSched& s) {
+                                                const TileSched& s, int, int) {
         const int row0 = m0 + q * 32;
         if (row0 >= s.M) return;
         const int row = row0 + st.lane;
