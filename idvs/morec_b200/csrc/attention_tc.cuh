@@ -19,8 +19,8 @@
 //     k' = t+4 <-> column 2t+1) on BOTH operands, which a sum over k does not notice;
 //   * backward: the transposed products (dK = dS^T Q, dV = P~^T dO) read dS / P~ from a [LP][LP+4] shared tile written
 //     once from the accumulator layout; warp w then owns the 16-KEY stripe.
-// Dropout keep bits: one Philox4x32 block per (pair, warp, n-tile, lane) = exactly the four accumulator elements of
-// that thread's 16x8 tile, identical in forward and backward.
+// Dropout keep bits: one Philox4x32-7 block per (pair, warp, n-tile PAIR, lane), 16 bits per decision = exactly the eight
+// accumulator elements of that thread's two 16x8 tiles, identical in forward and backward.
 #pragma once
 #include "attention_common.cuh"
 
@@ -246,14 +246,28 @@ __device__ __forceinline__ void tc_softmax_stripe(const TcAttnParams& p, float (
     }
 }
 
-// keep multipliers (0 or 1/(1-p)) of the four accumulator elements of n-tile n of this warp's stripe
-__device__ __forceinline__ void tc_keep4(const TcAttnParams& p, int pair, int nw, int nt, int warp, int n, int lane,
-                                         uint32_t th, float sc, float (&keep)[4]) {
-    const uint4 r = Philox::gen(p.seed, p.offset + (((uint64_t)pair * nw + warp) * nt + n) * 32 + lane);
-    keep[0] = r.x >= th ? sc : 0.f;
-    keep[1] = r.y >= th ? sc : 0.f;
-    keep[2] = r.z >= th ? sc : 0.f;
-    keep[3] = r.w >= th ? sc : 0.f;
+// keep multipliers (0 or 1/(1-p)) of the four accumulator elements of n-tiles 2*np and 2*np+1 of this warp's stripe:
+// one Philox4x32-7 block per (pair, warp, n-tile pair, lane), 16 bits per decision (common.cuh)
+__device__ __forceinline__ void tc_keep8(const TcAttnParams& p, int pair, int nw, int nt, int warp, int np, int lane,
+                                         uint32_t th16, float sc, float (&k0)[4], float (&k1)[4]) {
+    const uint4 r = Philox7::gen(p.seed, p.offset + (((uint64_t)pair * nw + warp) * (nt / 2) + np) * 32 + lane);
+    k0[0] = (r.x & 0xffffu) >= th16 ? sc : 0.f;  k1[0] = (r.x >> 16) >= th16 ? sc : 0.f;
+    k0[1] = (r.y & 0xffffu) >= th16 ? sc : 0.f;  k1[1] = (r.y >> 16) >= th16 ? sc : 0.f;
+    k0[2] = (r.z & 0xffffu) >= th16 ? sc : 0.f;  k1[2] = (r.z >> 16) >= th16 ? sc : 0.f;
+    k0[3] = (r.w & 0xffffu) >= th16 ? sc : 0.f;  k1[3] = (r.w >> 16) >= th16 ? sc : 0.f;
+}
+// all keep multipliers of a stripe (1 everywhere when dropout is off; tiles at or beyond `len` are left at 1)
+template <int NT>
+__device__ __forceinline__ void tc_keep_stripe(const TcAttnParams& p, int pair, int nw, int warp, int lane, int len,
+                                               float (&keep)[NT][4]) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) keep[n][0] = keep[n][1] = keep[n][2] = keep[n][3] = 1.f;
+    if (!(p.dropout_p > 0.f)) return;
+    const uint32_t th16 = drop_thresh16(p.dropout_p);
+    const float sc = 1.f / (1.f - p.dropout_p);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np)
+        if (np * 16 < len) tc_keep8(p, pair, nw, NT, warp, np, lane, th16, sc, keep[2 * np], keep[2 * np + 1]);
 }
 
 template <typename T, int D, int LP>
@@ -270,8 +284,6 @@ __global__ void __launch_bounds__(TcCfg<D, LP>::THREADS) attn_tc_fwd_kernel(cons
     const T* K = reinterpret_cast<const T*>(p.k);
     const T* V = reinterpret_cast<const T*>(p.v);
     T* O = reinterpret_cast<T*>(p.out);
-    const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
-    const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
     for (int s = blockIdx.x; s < p.n_seq; s += gridDim.x) {
         int row0, len;
         tc_range(p, s, LP, row0, len);
@@ -286,15 +298,12 @@ __global__ void __launch_bounds__(TcCfg<D, LP>::THREADS) attn_tc_fwd_kernel(cons
         tc_rows_dot_rows<D, LP>(Qs, Ks, m0, len, acc, g, t);
         tc_softmax_stripe<LP>(p, acc, s, h, m0, len, g, t);
         if (p.dropout_p > 0.f) {
-            const int pair = s * p.n_heads + h;
+            float keep[C::NT][4];
+            tc_keep_stripe<C::NT>(p, s * p.n_heads + h, C::NW, warp, lane, len, keep);
 #pragma unroll
             for (int n = 0; n < C::NT; ++n) {
-                if (n * 8 < len) {
-                    float keep[4];
-                    tc_keep4(p, pair, C::NW, C::NT, warp, n, lane, th, sc, keep);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[n][e] *= keep[e];
-                }
+                for (int e = 0; e < 4; ++e) acc[n][e] *= keep[n][e];
             }
         }
 #pragma unroll 1
@@ -327,8 +336,6 @@ __global__ void __launch_bounds__(TcCfg<D, LP>::THREADS) attn_tc_bwd_kernel(cons
     T* dQ = reinterpret_cast<T*>(p.dq);
     T* dK = reinterpret_cast<T*>(p.dk);
     T* dV = reinterpret_cast<T*>(p.dv);
-    const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
-    const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
     const int LL = p.seqlen * p.seqlen;
     if (p.dbias)
         for (int i = threadIdx.x; i < LL; i += C::THREADS) dB[i] = 0.f;
@@ -347,13 +354,13 @@ __global__ void __launch_bounds__(TcCfg<D, LP>::THREADS) attn_tc_bwd_kernel(cons
             tc_rows_dot_rows<D, LP>(Qs, Ks, m0, len, pr, g, t);
             tc_softmax_stripe<LP>(p, pr, s, h, m0, len, g, t);
             tc_rows_dot_rows<D, LP>(Gs, Vs, m0, len, dp, g, t);          // dP~ = dO . V^T
-            const int pair = s * p.n_heads + h;
+            float keepm[C::NT][4];
+            tc_keep_stripe<C::NT>(p, s * p.n_heads + h, C::NW, warp, lane, len, keepm);
             float dsum[2] = {0.f, 0.f};
 #pragma unroll
             for (int n = 0; n < C::NT; ++n) {
                 if (n * 8 < len) {
-                    float keep[4] = {1.f, 1.f, 1.f, 1.f};
-                    if (p.dropout_p > 0.f) tc_keep4(p, pair, C::NW, C::NT, warp, n, lane, th, sc, keep);
+                    const float (&keep)[4] = keepm[n];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         dp[n][e] *= keep[e];                             // dP

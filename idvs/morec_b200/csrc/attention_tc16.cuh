@@ -161,8 +161,6 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(
     const T* K = reinterpret_cast<const T*>(p.k);
     const T* V = reinterpret_cast<const T*>(p.v);
     T* O = reinterpret_cast<T*>(p.out);
-    const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
-    const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
     for (int s = blockIdx.x; s < p.n_seq; s += gridDim.x) {
         int row0, len;
         tc_range(p, s, LP, row0, len);
@@ -178,15 +176,12 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(
         tc16_rows_dot_rows<D, LP>(Qs, Ks, m0, len, acc, lane);
         tc_softmax_stripe<LP>(p, acc, s, h, m0, len, g, t);
         if (p.dropout_p > 0.f) {
-            const int pair = s * p.n_heads + h;
+            float keep[C::NT][4];
+            tc_keep_stripe<C::NT>(p, s * p.n_heads + h, C::NW, warp, lane, len, keep);
 #pragma unroll
             for (int n = 0; n < C::NT; ++n) {
-                if (n * 8 < len) {
-                    float keep[4];
-                    tc_keep4(p, pair, C::NW, C::NT, warp, n, lane, th, sc, keep);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[n][e] *= keep[e];
-                }
+                for (int e = 0; e < 4; ++e) acc[n][e] *= keep[n][e];
             }
         }
         float o[C::MT][4];
@@ -217,8 +212,6 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
     T* dQ = reinterpret_cast<T*>(p.dq);
     T* dK = reinterpret_cast<T*>(p.dk);
     T* dV = reinterpret_cast<T*>(p.dv);
-    const uint32_t th = (uint32_t)fminf(p.dropout_p * 4294967296.f, 4294967295.f);
-    const float sc = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
     const int LL = p.seqlen * p.seqlen;
     if (p.dbias)
         for (int i = threadIdx.x; i < LL; i += C::THREADS) dB[i] = 0.f;
@@ -238,13 +231,13 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
             tc16_rows_dot_rows<D, LP>(Qs, Ks, m0, len, pr, lane);
             tc_softmax_stripe<LP>(p, pr, s, h, m0, len, g, t);
             tc16_rows_dot_rows<D, LP>(Gs, Vs, m0, len, dp, lane);        // dP~ = dO . V^T
-            const int pair = s * p.n_heads + h;
+            float keepm[C::NT][4];
+            tc_keep_stripe<C::NT>(p, s * p.n_heads + h, C::NW, warp, lane, len, keepm);
             float dsum[2] = {0.f, 0.f};
 #pragma unroll
             for (int n = 0; n < C::NT; ++n) {
-                float keep[4] = {1.f, 1.f, 1.f, 1.f};
+                const float (&keep)[4] = keepm[n];
                 if (n * 8 < len) {
-                    if (p.dropout_p > 0.f) tc_keep4(p, pair, C::NW, C::NT, warp, n, lane, th, sc, keep);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         dp[n][e] *= keep[e];                             // dP

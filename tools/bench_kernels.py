@@ -72,6 +72,13 @@ with lib.fp32_mode(False):
     dg, db, dbi = (torch.zeros(H, device="cuda") for _ in range(3))
     timeit("ln bwd (dy+dy2, dropout 0.1)", lambda: lib.layernorm_bwd(x, y, g, b, rstd, dy2=r, dgamma=dg, dbeta=db, dbias=dbi, p_pre=0.1,
                                                                      seed=1, off_pre=1 << 36), bytes_=n_tok * 5 * H * es)
+    timeit("ln fwd (residual, no dropout)", lambda: lib.layernorm_fwd(x, g, b, 1e-12, residual=r, out=y), bytes_=n_tok * 3 * H * es)
+    timeit("ln bwd (dy+dy2, no dropout)", lambda: lib.layernorm_bwd(x, y, g, b, rstd, dy2=r, dgamma=dg, dbeta=db, dbias=dbi),
+           bytes_=n_tok * 4 * H * es)
+    kw0 = dict(kw); kw0["dropout_p"] = 0.0
+    timeit("attn fwd (no dropout)", lambda: lib.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, **kw0), bytes_=n_tok * 4 * H * es)
+    timeit("attn bwd (no dropout)", lambda: lib.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H],
+                                                        dqkv[:, 2 * H:], **kw0), bytes_=n_tok * 7 * H * es)
     # GEMMs of the FFN
     w_i = (torch.randn(I, H, device="cuda") * 0.02).to(dt)
     w_o = (torch.randn(H, I, device="cuda") * 0.02).to(dt)
