@@ -40,7 +40,7 @@ extern "C" int morec_bert_layer_fwd(const MorecBertLayerFwd* a, void* stream) {
                    MOREC_EPI_LINEAR, 1.f, 0, stream));
     RUN(morec_layernorm_fwd(a->tmp_h, a->x, nullptr, 0, a->g1, a->b1, a->x1, nullptr, a->rstd1, M, H, a->eps, st,
                             a->p_hidden, 0.f, a->seed, a->off_ln1, 0, stream));
-    RUN(morec_gemm(a->x1, a->w_i, a->act, a->pre, a->b_i, nullptr, M, I, H, H, H, I, 0, 0, 0, a->dtype, obf, MOREC_EPI_GELU,
+    RUN(morec_gemm(a->x1, a->w_i, a->act, a->pre, a->b_i, nullptr, M, I, H, H, H, I, 0, 0, 0, a->dtype, obf, MOREC_EPI_GELU_DGELU,
                    1.f, 0, stream));
     RUN(morec_gemm(a->act, a->w_o, a->tmp_h, nullptr, a->b_o, nullptr, M, H, I, I, I, H, 0, 0, 0, a->dtype, obf,
                    MOREC_EPI_LINEAR, 1.f, 0, stream));
@@ -62,11 +62,11 @@ extern "C" int morec_bert_layer_bwd(const MorecBertLayerBwd* a, void* stream) {
     void* dfo = drop ? a->dbr : a->dz2;
     RUN(morec_layernorm_bwd(a->dy, a->dy2, f->x2, f->g2, f->b2, f->rstd2, a->dz2, drop ? a->dbr : nullptr, a->dg2, a->db2,
                             a->db_o, nullptr, 0, M, H, st, f->p_hidden, 0.f, f->seed, f->off_ln2, 0, stream));
-    // ---- FFN2: dWo2 += dfo^T act ; dpre = (dfo Wo2) * gelu'(pre)
+    // ---- FFN2: dWo2 += dfo^T act ; dpre = (dfo Wo2) * gelu'(pre)   (`pre` holds gelu'(pre-activation), saved by the forward)
     RUN(morec_gemm(dfo, f->act, a->dw_o, nullptr, nullptr, nullptr, H, I, M, H, I, I, 0, 1, 1, f->dtype, 0,
                    MOREC_EPI_LINEAR, 1.f, 1, stream));
     RUN(morec_gemm(dfo, f->w_o, a->dpre, nullptr, nullptr, f->pre, M, I, H, H, I, I, I, 0, 1, f->dtype, obf,
-                   MOREC_EPI_MUL_GELU_GRAD, 1.f, 0, stream));
+                   MOREC_EPI_MUL_AUX, 1.f, 0, stream));
     // ---- FFN1: dbi, dWi, dx1 (branch)
     RUN(morec_colsum(a->dpre, a->db_i, M, I, I, st, stream));
     RUN(morec_gemm(a->dpre, f->x1, a->dw_i, nullptr, nullptr, nullptr, I, H, M, I, H, H, 0, 1, 1, f->dtype, 0,

@@ -118,6 +118,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tfull_bar = bars + 2 * C::STAGES;
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* aux_bars = bars + 32;               // [8] one per epilogue warp: side-input TMA loads
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,6 +140,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(smem_u32(&tfull_bar[s]), 1);
             mbar_init(smem_u32(&tempty_bar[s]), 2 * kEpiWarps * Epi::kGroups);
         }
+        for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&aux_bars[s]), 1);
         mbar_fence_init();
     }
     cluster_sync_all();                       // barrier inits of both CTAs visible before any remote arrive / TMA
@@ -243,6 +245,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         st.bufs = epi_base + (cg * 4 + q) * (NSUB * kEpiBufBytes);
         st.nsub = NSUB;
         st.grp = 0;
+        st.aux_bar = smem_u32(&aux_bars[warp - 4]); st.aux_phase = 0; st.aux_groups = 0;
         st.c_end = 0;
         st.lane = lane;
         int acc = 0;
@@ -262,6 +265,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 Epi::template prefetch<C::BLOCK_N>(ep, (nt / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
                                                    (nt % p.n_tiles) * C::BLOCK_N, p);
             }
+            Epi::template pre_tile<KIND, C::BLOCK_N>(ep, tmC2, st, m0, q, n0, p, cg, Epi::kGroups);
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
             Epi::template tile<KIND, C::BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::BLOCK_N, st, m0, q,
@@ -305,9 +309,16 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     } else {
         tmC = tmA;
     }
+    bool aux_tma = false;
     if (g.C2) {
         rc = make_tmap_2d(&tmC2, g.C2, g.out_bf16 != 0, g.N, g.M, (uint64_t)g.ldc * out_elem, out_cols, 32);
         if (rc) return rc;
+    } else if (Epi::kAuxMode && g.aux && bf && g.out_bf16 && (g.ldaux % 8) == 0 &&
+               (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0) {
+        // side input of the activation-gradient epilogues, staged by TMA in the boxes of the output (32 rows x 128 B)
+        rc = make_tmap_2d(&tmC2, g.aux, true, g.N, g.M, (uint64_t)g.ldaux * 2, out_cols, 32);
+        if (rc) return rc;
+        aux_tma = true;
     } else {
         tmC2 = tmC;
     }
@@ -319,6 +330,7 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     p.a_mn = g.a_mn; p.b_mn = g.b_mn;
     p.accumulate = g.accumulate;
     p.out_bf16 = g.out_bf16;
+    p.aux_tma = aux_tma ? 1 : 0;
     const int pairs_max = num_sms() / 2;
     int splits = 1;
     if (g.accumulate && g.allow_split_k) {

@@ -22,8 +22,8 @@ struct StdEpiParams {
 template <int MODE>
 struct StdEpi {
     using Params = StdEpiParams;
-    static constexpr bool kAuxMode = MODE == MOREC_EPI_MUL_GELU_GRAD || MODE == MOREC_EPI_MUL_RELU_GRAD;
-    static constexpr int kStreams = MODE == MOREC_EPI_GELU ? 2 : 1;
+    static constexpr bool kAuxMode = MODE == MOREC_EPI_MUL_GELU_GRAD || MODE == MOREC_EPI_MUL_RELU_GRAD || MODE == MOREC_EPI_MUL_AUX;
+    static constexpr int kStreams = (MODE == MOREC_EPI_GELU || MODE == MOREC_EPI_GELU_DGELU) ? 2 : 1;
     static constexpr int kGroups = 2;      // CTA-pair kernel: two epilogue warp groups, half of the tile's columns each
 
     __device__ __forceinline__ static void load_aux(const Params& ep, float (&a)[32], int row, int col0, int M, int N) {
@@ -86,6 +86,52 @@ struct StdEpi {
         return __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
     }
 
+    // this warp's chunk range [c_lo, c_end) of the tile at n0 (column group cg of ncg)
+    template <int BLOCK_N>
+    __device__ __forceinline__ static void chunk_range(const TileSched& s, int n0, int cg, int ncg, int& c_lo, int& c_end) {
+        c_end = (s.N - n0 + 31) / 32;
+        if (c_end > BLOCK_N / 32) c_end = BLOCK_N / 32;
+        if (s.out_bf16) c_end = (c_end + 1) & ~1;
+        c_lo = cg * (BLOCK_N / 32) / ncg;
+        const int c_hi = (cg + 1) * (BLOCK_N / 32) / ncg;
+        if (c_end > c_hi) c_end = c_hi;
+    }
+
+    // Side input by TMA (CTA-pair kernel, bf16): before the wait for the tile's accumulator, stage this warp's
+    // 32 rows x (its columns) of aux into its own staging sub-buffers -- the very boxes (and swizzle) the result will be
+    // stored from, so the epilogue reads aux from shared memory and overwrites it in place.  Per-thread global loads
+    // of a row-per-thread layout touched 32 cache lines per instruction and were exposed to their full latency
+    // (measured: 93 us for dgrad * aux against 52 us for the plain dgrad).
+    template <int KIND, int BLOCK_N>
+    __device__ __forceinline__ static void pre_tile(const Params& ep, const CUtensorMap& tmAux, EpiStore& st, int m0, int q,
+                                                    int n0, const TileSched& s, int cg, int ncg) {
+        st.aux_groups = 0;
+        if constexpr (kAuxMode) {
+            if (!s.aux_tma || st.aux_bar == 0) return;
+            const int row0 = m0 + q * 32;
+            if (row0 >= s.M) return;
+            int c_lo, c_end;
+            chunk_range<BLOCK_N>(s, n0, cg, ncg, c_lo, c_end);
+            const int ng = (c_end - c_lo + 1) / 2;                // 64-column (two-chunk) groups = sub-buffers
+            if (ng <= 0 || ng > st.nsub) return;
+            if (st.lane == 0) {
+                tma_store_wait_read<0>();                         // both staging halves are free again
+                mbar_expect_tx(st.aux_bar, (uint32_t)ng * kEpiBufBytes);
+                for (int i = 0; i < ng; ++i)
+                    tma_load_2d(&tmAux, st.aux_bar, smem_u32(st.bufs + ((st.grp + i) & 1) * kEpiBufBytes),
+                                n0 + (c_lo + 2 * i) * 32, row0);
+            }
+            __syncwarp();
+            st.aux_groups = ng;
+        }
+    }
+    // packed side input of chunk c from the staging sub-buffer the result of this chunk will be written to
+    __device__ __forceinline__ static void load_aux_smem(const EpiStore& st, uint4 (&r)[4], int c) {
+        const uint8_t* rowp = st.bufs + (st.grp & 1) * kEpiBufBytes + st.lane * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = *reinterpret_cast<const uint4*>(rowp + ((((c & 1) << 2) + j) ^ (st.lane & 7)) * 16);
+    }
+
     // one tile ahead: pull this thread's row of the side input (aux) for columns [n0, n0 + BLOCK_N) into L2
     template <int BLOCK_N>
     __device__ __forceinline__ static void prefetch(const Params& ep, int row, int n0, const TileSched& s) {
@@ -125,6 +171,33 @@ struct StdEpi {
             st.put(&tmC2, x, c, obf, 1, 2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = FAST ? gelu_fast(x[j]) : gelu_erf(x[j]);
+        } else if constexpr (MODE == MOREC_EPI_GELU_DGELU) {
+            // activation derivative to C2 (the backward multiplies by it), activation to C; both from one erfc / exp
+            float d[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if constexpr (FAST) {
+                    float q, e;
+                    gelu_fast_parts(x[j], q, e);
+                    const float cdf = x[j] < 0.f ? q : 1.0f - q;
+                    d[j] = fmaf(x[j], 0.39894228040143267794f * e, cdf);
+                    x[j] = fmaf(-fabsf(x[j]), q, fmaxf(x[j], 0.f));
+                } else {
+                    d[j] = gelu_erf_grad(x[j]);
+                    x[j] = gelu_erf(x[j]);
+                }
+            }
+            st.put(&tmC2, d, c, obf, 1, 2);
+        } else if constexpr (MODE == MOREC_EPI_MUL_AUX) {
+            if (have_raw) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] *= aux_raw_at(araw, j);
+            } else {
+                float a[32];
+                load_aux(ep, a, row, col0, s.M, s.N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] *= a[j];
+            }
         } else if constexpr (MODE == MOREC_EPI_GELU_NOSAVE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = FAST ? gelu_fast(x[j]) : gelu_erf(x[j]);
@@ -168,38 +241,42 @@ struct StdEpi {
         const int row0 = m0 + q * 32;
         if (row0 >= s.M) return;   // warp-uniform
         const int row = row0 + st.lane;
-        int c_end = (s.N - n0 + 31) / 32;
-        if (c_end > BLOCK_N / 32) c_end = BLOCK_N / 32;
-        if (s.out_bf16) c_end = (c_end + 1) & ~1;
-        const int c_lo = cg * (BLOCK_N / 32) / ncg;                 // this warp's column group
-        const int c_hi = (cg + 1) * (BLOCK_N / 32) / ncg;
-        if (c_end > c_hi) c_end = c_hi;
+        int c_lo, c_end;
+        chunk_range<BLOCK_N>(s, n0, cg, ncg, c_lo, c_end);
         if (c_lo >= c_end) return;
         st.c_end = c_end;
         const bool add_bias = ep.bias != nullptr && split == 0;
         // software pipeline: the TMEM load (and the packed bf16 side input) of chunk c+1 is in flight while chunk c is
         // processed
-        const bool raw = aux_raw_ok(ep, s);
+        const bool tma_aux = st.aux_groups > 0;
+        if (tma_aux) {                                  // side input staged by pre_tile(): wait for it to land
+            mbar_wait(st.aux_bar, st.aux_phase);
+            st.aux_phase ^= 1;
+        }
+        const bool direct = !tma_aux && aux_raw_ok(ep, s);
+        const bool raw = tma_aux || direct;
         uint4 ra[4], rb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) ra[j] = rb[j] = make_uint4(0u, 0u, 0u, 0u);
         uint32_t va[32], vb[32];
-        if (raw) load_aux_raw(ep, ra, row, n0 + c_lo * 32, s.M);
+        if (direct) load_aux_raw(ep, ra, row, n0 + c_lo * 32, s.M);
         tmem_ld32(taddr + c_lo * 32, va);
 #pragma unroll 1
         for (int c = c_lo; c < c_end; c += 2) {
             tc_wait_ld();
             if (c + 1 < c_end) {
                 tmem_ld32(taddr + (c + 1) * 32, vb);
-                if (raw) load_aux_raw(ep, rb, row, n0 + (c + 1) * 32, s.M);
+                if (direct) load_aux_raw(ep, rb, row, n0 + (c + 1) * 32, s.M);
             }
+            if (tma_aux) load_aux_smem(st, ra, c);
             chunk<FAST>(ep, tmC, tmC2, st, va, c, row, row0, n0, add_bias, s, ra, raw);
             if (c + 1 < c_end) {
                 tc_wait_ld();
                 if (c + 2 < c_end) {
                     tmem_ld32(taddr + (c + 2) * 32, va);
-                    if (raw) load_aux_raw(ep, ra, row, n0 + (c + 2) * 32, s.M);
+                    if (direct) load_aux_raw(ep, ra, row, n0 + (c + 2) * 32, s.M);
                 }
+                if (tma_aux) load_aux_smem(st, rb, c + 1);
                 chunk<FAST>(ep, tmC, tmC2, st, vb, c + 1, row, row0, n0, add_bias, s, rb, raw);
             }
         }
@@ -214,6 +291,8 @@ MOREC_DECLARE_STD_GEMM(2)
 MOREC_DECLARE_STD_GEMM(3)
 MOREC_DECLARE_STD_GEMM(4)
 MOREC_DECLARE_STD_GEMM(5)
+MOREC_DECLARE_STD_GEMM(6)
+MOREC_DECLARE_STD_GEMM(7)
 #define MOREC_DEFINE_STD_GEMM(MODE)                                                                     \
     namespace morec {                                                                                   \
     int gemm_std_run_##MODE(const GemmArgs& g, const StdEpiParams& ep, cudaStream_t stream) {           \

@@ -64,10 +64,11 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
                           int dtype, int out_bf16, int epilogue, float alpha, int accumulate, void* stream) {
     using namespace morec;
     MOREC_CHECK_ARG(A && B && C, "morec_gemm: null operand");
-    MOREC_CHECK_ARG(epilogue >= MOREC_EPI_LINEAR && epilogue <= MOREC_EPI_MUL_RELU_GRAD, "morec_gemm: bad epilogue %d",
+    MOREC_CHECK_ARG(epilogue >= MOREC_EPI_LINEAR && epilogue <= MOREC_EPI_MUL_AUX, "morec_gemm: bad epilogue %d",
                     epilogue);
-    MOREC_CHECK_ARG(epilogue != MOREC_EPI_GELU || C2, "morec_gemm: EPI_GELU needs C2 (pre-activation output)");
-    MOREC_CHECK_ARG((epilogue != MOREC_EPI_MUL_GELU_GRAD && epilogue != MOREC_EPI_MUL_RELU_GRAD) || aux,
+    MOREC_CHECK_ARG((epilogue != MOREC_EPI_GELU && epilogue != MOREC_EPI_GELU_DGELU) || C2,
+                    "morec_gemm: EPI_GELU / EPI_GELU_DGELU need C2 (second output)");
+    MOREC_CHECK_ARG((epilogue != MOREC_EPI_MUL_GELU_GRAD && epilogue != MOREC_EPI_MUL_RELU_GRAD && epilogue != MOREC_EPI_MUL_AUX) || aux,
                     "morec_gemm: activation-gradient epilogue needs aux");
     MOREC_CHECK_ARG(!(accumulate && epilogue != MOREC_EPI_LINEAR), "morec_gemm: accumulate only with EPI_LINEAR");
     GemmArgs g;
@@ -77,6 +78,7 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
     g.a_mn = a_mn_major; g.b_mn = b_mn_major;
     g.dtype = dtype; g.out_bf16 = out_bf16;
     g.accumulate = accumulate; g.allow_split_k = accumulate;
+    g.aux = aux; g.ldaux = ldaux;
     StdEpiParams ep;
     ep.mode = epilogue; ep.alpha = alpha; ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux;
     ep.aux_bf16 = (dtype == 1);
@@ -87,6 +89,8 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
         case MOREC_EPI_GELU_NOSAVE: return gemm_std_run_2(g, ep, st);
         case MOREC_EPI_RELU: return gemm_std_run_3(g, ep, st);
         case MOREC_EPI_MUL_GELU_GRAD: return gemm_std_run_4(g, ep, st);
-        default: return gemm_std_run_5(g, ep, st);
+        case MOREC_EPI_MUL_RELU_GRAD: return gemm_std_run_5(g, ep, st);
+        case MOREC_EPI_GELU_DGELU: return gemm_std_run_6(g, ep, st);
+        default: return gemm_std_run_7(g, ep, st);
     }
 }

@@ -36,6 +36,8 @@ struct GemmArgs {
     int out_bf16;          // output element type of C/C2 (0: fp32, 1: bf16)
     int accumulate;        // 1: C += result via TMA reduce-add (C must be fp32); enables split-K
     int allow_split_k;
+    const void* aux = nullptr;   // epilogue side input [M, ldaux] (activation-gradient epilogues), element type of the operands
+    int ldaux = 0;
 };
 
 constexpr int BLOCK_M = 128;
@@ -52,6 +54,7 @@ struct TileSched {
     int a_mn, b_mn;
     int accumulate;
     int out_bf16;
+    int aux_tma;           // 1: tmC2 describes the epilogue side input (bf16) and the CTA-pair kernel stages it by TMA
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -107,6 +110,9 @@ struct EpiStore {
     int nsub;                 // sub-buffers owned by this warp (2 in the single-CTA kernels, 4 in the CTA-pair kernel)
     int c_end;                // number of 32-column chunks of the current tile (set by the epilogue)
     int grp;                  // flushed-group counter: selects the staging half
+    uint32_t aux_bar;         // mbarrier of this warp's side-input TMA loads (0: not used by this kernel)
+    uint32_t aux_phase;
+    int aux_groups;           // side-input groups staged for the current tile (0: read the side input directly)
     const CUtensorMap* tm[2]; // output tensor map per stream (0: C, 1: C2)
 
     // The staging memory is used as TWO halves when it has at least two sub-buffers per output stream: a group is
@@ -195,6 +201,10 @@ struct EpiStore {
 //     static constexpr int kGroups;                      // epilogue warp groups the CTA-pair kernel should run (1 or 2) }
 //     template <int BLOCK_N> static __device__ void prefetch(const Params&, int row, int n0, const TileSched&);
 //   taddr already includes the warp's lane quarter and the accumulator stage; thread `lane` owns row m0+q*32+lane.
+//     template <int KIND, int BLOCK_N> static __device__ void pre_tile(const Params&, const CUtensorMap& tmC2, EpiStore&,
+//                                 int m0, int q, int n0, const TileSched&, int cg, int ncg);
+//   pre_tile() runs right BEFORE the wait for the tile's accumulator (CTA-pair kernel only): TMA loads issued here
+//   land while the tensor core still works on the tile.
 //   prefetch() is called one tile ahead: it may pull the epilogue's side inputs of (row, [n0, n0+BLOCK_N)) into L2.
 
 template <int KIND, int BLOCK_N, class Epi>
@@ -375,6 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         st.bufs = epi_base + q * (C::EPI_BUFS * kEpiBufBytes);
         st.nsub = C::EPI_BUFS;
         st.grp = 0;
+        st.aux_bar = 0; st.aux_phase = 0; st.aux_groups = 0;
         st.c_end = 0;
         st.lane = lane;
         int acc = 0;
@@ -457,6 +468,7 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
     p.a_mn = g.a_mn; p.b_mn = g.b_mn;
     p.accumulate = g.accumulate;
     p.out_bf16 = g.out_bf16;
+    p.aux_tma = 0;
     const int sms = num_sms();
     int splits = 1;
     if (g.accumulate && g.allow_split_k) {

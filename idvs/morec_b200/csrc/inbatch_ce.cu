@@ -65,6 +65,10 @@ struct CeParams {
 struct CeFwdEpi {
     using Params = CeParams;
     static constexpr int kGroups = 1;      // row statistics span the whole tile: one warp per row quarter
+    static constexpr bool kAuxMode = false;
+    template <int KIND, int BLOCK_N>
+    __device__ __forceinline__ static void pre_tile(const Params&, const CUtensorMap&, EpiStore&, int, int, int,
+                                                    const TileSched&, int, int) {}
     template <int BLOCK_N>
     __device__ __forceinline__ static void prefetch(const Params&, int, int, const TileSched&) {}
     template <int KIND, int BLOCK_N>
@@ -118,6 +122,10 @@ struct CeFwdEpi {
 struct CeBwdEpi {
     using Params = CeParams;
     static constexpr int kGroups = 1;
+    static constexpr bool kAuxMode = false;
+    template <int KIND, int BLOCK_N>
+    __device__ __forceinline__ static void pre_tile(const Params&, const CUtensorMap&, EpiStore&, int, int, int,
+                                                    const TileSched&, int, int) {}
     template <int BLOCK_N>
     __device__ __forceinline__ static void prefetch(const Params&, int, int, const TileSched&) {}
     template <int KIND, int BLOCK_N>

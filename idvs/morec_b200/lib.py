@@ -239,7 +239,7 @@ def d2h_many(tensors):
 
 
 # enum mirrors
-EPI_LINEAR, EPI_GELU, EPI_GELU_NOSAVE, EPI_RELU, EPI_MUL_GELU_GRAD, EPI_MUL_RELU_GRAD = range(6)
+EPI_LINEAR, EPI_GELU, EPI_GELU_NOSAVE, EPI_RELU, EPI_MUL_GELU_GRAD, EPI_MUL_RELU_GRAD, EPI_GELU_DGELU, EPI_MUL_AUX = range(8)
 DT_F32, DT_BF16 = 0, 1
 
 

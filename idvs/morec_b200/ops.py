@@ -263,7 +263,7 @@ class BertTowerFn(torch.autograd.Function):
                                                  seed=drop.seed, off_pre=drop.off(2 + 4 * l))
                 del ao
                 pre = torch.empty(n_tok, I, device=dev, dtype=adt)
-                act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU, pre=pre)
+                act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU_DGELU, pre=pre)   # pre <- gelu'(z)
                 fo = lib.linear_fwd(act, w_o, ob.detach())
                 x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
                                                  seed=drop.seed, off_pre=drop.off(3 + 4 * l))
@@ -373,7 +373,7 @@ class BertTowerFn(torch.autograd.Function):
             # FFN2 / FFN1
             dow = _z(ow)
             lib.linear_wgrad(dfo, act, dow)
-            dpre_i = lib.linear_dgrad(dfo, w_o, epilogue=lib.EPI_MUL_GELU_GRAD, aux=pre)
+            dpre_i = lib.linear_dgrad(dfo, w_o, epilogue=lib.EPI_MUL_AUX, aux=pre)
             if dfo is not dz2:
                 del dfo
             dib, diw = _z(ib), _z(iw)

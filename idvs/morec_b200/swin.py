@@ -156,7 +156,7 @@ class SwinTowerFn(torch.autograd.Function):
                 z, _, rstd_a = lib.layernorm_fwd(x1, P(m.layernorm_after.weight), P(m.layernorm_after.bias), eps)
                 w_i, w_o = _cw(m.intermediate.dense.weight, adt), _cw(m.output.dense.weight, adt)
                 pre = torch.empty(z.shape[0], w_i.shape[0], device=dev, dtype=adt)
-                u = lib.linear_fwd(z, w_i, P(m.intermediate.dense.bias), epilogue=lib.EPI_GELU, pre=pre)
+                u = lib.linear_fwd(z, w_i, P(m.intermediate.dense.bias), epilogue=lib.EPI_GELU_DGELU, pre=pre)   # pre <- gelu'(z)
                 mo = lib.linear_fwd(u, w_o, P(m.output.dense.bias))
                 x2 = lib.scale_add_rows(mo, x=x1)
                 srec["blocks"].append(dict(y=y, rstd_b=rstd_b, yw=yw, qkv=qkv, bias=bias, mask=mask, perm=perm, inv=inv,
@@ -238,7 +238,7 @@ class SwinTowerFn(torch.autograd.Function):
                 # ---- MLP branch:  x2 = x1 + W2 gelu(W1 LN(x1))
                 lib.linear_wgrad(dx, rec["u"], G(m.output.dense.weight))
                 lib.colsum(dx, G(m.output.dense.bias))
-                dpre = lib.linear_dgrad(dx, w_o, epilogue=lib.EPI_MUL_GELU_GRAD, aux=rec["pre"])
+                dpre = lib.linear_dgrad(dx, w_o, epilogue=lib.EPI_MUL_AUX, aux=rec["pre"])
                 lib.linear_wgrad(dpre, rec["z"], G(m.intermediate.dense.weight))
                 lib.colsum(dpre, G(m.intermediate.dense.bias))
                 dz = lib.linear_dgrad(dpre, w_i)

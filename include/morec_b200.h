@@ -43,7 +43,8 @@ int morec_device_sms(void);
  *     dgrad    dx = dy W        : A=dy (0), B=W stored [N_out,K_in] = "[K,N]" of this GEMM (1)
  *     wgrad    dW += dy^T x     : A=dy stored [M,N_out] (1), B=x stored [M,K_in] (1), accumulate=1 (split-K,
  *                                 TMA reduce-add into fp32 dW)
- * epilogue: see MOREC_EPI_*.  C2 receives the pre-activation for MOREC_EPI_GELU (needed by the backward).
+ * epilogue: see MOREC_EPI_*.  C2 receives the pre-activation for MOREC_EPI_GELU, the activation derivative for
+ * MOREC_EPI_GELU_DGELU (needed by the backward).
  * aux ([M,ldaux], same dtype as the operands) feeds the activation-gradient epilogues.
  * out_bf16 selects the element type of C/C2 (fp32 or bf16).  accumulate requires fp32 C and EPI_LINEAR.
  */
@@ -53,7 +54,11 @@ enum {
     MOREC_EPI_GELU_NOSAVE = 2,   /* C = gelu_erf(alpha*acc + bias)                (encoders.py:69-70 eval) */
     MOREC_EPI_RELU = 3,          /* C = relu(alpha*acc + bias)                    (modules.py:16)          */
     MOREC_EPI_MUL_GELU_GRAD = 4, /* C = alpha*acc * gelu_erf'(aux)   aux = saved pre-activation            */
-    MOREC_EPI_MUL_RELU_GRAD = 5  /* C = alpha*acc * (aux > 0)        aux = saved relu output               */
+    MOREC_EPI_MUL_RELU_GRAD = 5, /* C = alpha*acc * (aux > 0)        aux = saved relu output               */
+    MOREC_EPI_GELU_DGELU = 6,    /* z = alpha*acc + bias ; C = gelu_erf(z) ; C2 = gelu_erf'(z): the forward saves
+                                    the activation DERIVATIVE instead of the pre-activation (they share the
+                                    exponential), so the backward epilogue is a plain multiply             */
+    MOREC_EPI_MUL_AUX = 7        /* C = alpha*acc * aux              aux = C2 of MOREC_EPI_GELU_DGELU      */
 };
 int morec_gemm(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M, int N,
                int K, int lda, int ldb, int ldc, int ldaux, int a_mn_major, int b_mn_major, int dtype, int out_bf16,

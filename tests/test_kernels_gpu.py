@@ -54,6 +54,13 @@ def _epilogue_checks(lib, dt, tol):
     F.gelu(a64).sum().backward()
     assert rel(lib.linear_dgrad(dy, w, epilogue=lib.EPI_MUL_GELU_GRAD, aux=aux), (dy.double() @ w.double()) * a64.grad) < tol
     assert rel(lib.linear_dgrad(dy, w, epilogue=lib.EPI_MUL_RELU_GRAD, aux=aux), (dy.double() @ w.double()) * (aux.double() > 0)) < tol
+    assert rel(lib.linear_dgrad(dy, w, epilogue=lib.EPI_MUL_AUX, aux=aux), (dy.double() @ w.double()) * aux.double()) < tol
+    # forward that saves gelu'(z) instead of z (what the BERT / Swin FFN uses): the pair (GELU_DGELU, MUL_AUX) must equal autograd
+    dact = torch.empty(M, N, device="cuda", dtype=dt)
+    y2 = lib.linear_fwd(x, w, b, epilogue=lib.EPI_GELU_DGELU, pre=dact)
+    rp64 = rp.detach().requires_grad_(True)
+    F.gelu(rp64).sum().backward()
+    assert rel(y2, F.gelu(rp)) < tol and rel(dact, rp64.grad) < tol
     dw = torch.full((N, K), 2.0, device="cuda")
     lib.linear_wgrad(dy, x, dw)
     assert rel(dw, dy.double().t() @ x.double() + 2.0) < tol

@@ -87,9 +87,11 @@ with lib.fp32_mode(False):
     act = torch.empty(n_tok, I, device="cuda", dtype=dt)
     fl = 2.0 * n_tok * H * I
     timeit("FFN1 fwd (GELU, 2 outputs)", lambda: lib.linear_fwd(x, w_i, bi, epilogue=lib.EPI_GELU, pre=pre, out=act), flops=fl)
+    timeit("FFN1 fwd (GELU + GELU' outputs)", lambda: lib.linear_fwd(x, w_i, bi, epilogue=lib.EPI_GELU_DGELU, pre=pre, out=act), flops=fl)
     timeit("FFN1 fwd (plain bias)", lambda: lib.linear_fwd(x, w_i, bi, out=act), flops=fl)
     timeit("FFN2 fwd (plain bias)", lambda: lib.linear_fwd(act, w_o, g, out=y), flops=fl)
     timeit("dpre = (dy Wo2) * gelu'(pre)", lambda: lib.linear_dgrad(x, w_o, epilogue=lib.EPI_MUL_GELU_GRAD, aux=pre, out=act), flops=fl)
+    timeit("dpre = (dy Wo2) * aux", lambda: lib.linear_dgrad(x, w_o, epilogue=lib.EPI_MUL_AUX, aux=pre, out=act), flops=fl)
     timeit("dgrad plain same shape", lambda: lib.linear_dgrad(x, w_o, out=act), flops=fl)
     dw = torch.zeros(I, H, device="cuda")
     timeit("wgrad dW_i (split-K)", lambda: lib.linear_wgrad(act, x, dw), flops=fl)
