@@ -71,6 +71,44 @@ __global__ void bert_embed_bwd_kernel(const T* __restrict__ dz, const int64_t* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------- token packing plan
+// The text tower runs on PACKED tokens (only real word pieces of non-pad items).  The host needs just one number per
+// item to lay the batch out -- its count of real tokens (n x int32 instead of the n x T attention mask) -- and a
+// prefix sum; which word piece goes where is resolved on the device.  Replaces the token-level index arithmetic the
+// host used to do between the size-determining sync and the first layer (the GPU idles there).
+__global__ void mask_row_lens_kernel(const int64_t* __restrict__ text, int ld, int T, int n, int32_t* __restrict__ lens) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int64_t* m = text + (size_t)warp * ld + T;          // attention-mask half of the row (run.py:93-98)
+    int cnt = 0;
+    for (int c = lane; c < T; c += 32) cnt += m[c] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) lens[warp] = cnt;
+}
+
+// one warp per encoded item s: its kept word pieces (attention mask != 0), in column order, go to rows
+// [cu[s], cu[s+1]) of tok_ids / tok_pos (tok_pos = original column, so position embeddings equal HF's)
+__global__ void pack_tokens_kernel(const int64_t* __restrict__ text, int ld, int T, const int32_t* __restrict__ enc_rows,
+                                   const int32_t* __restrict__ cu, int n_enc, int64_t* __restrict__ tok_ids,
+                                   int32_t* __restrict__ tok_pos) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_enc) return;
+    const int64_t* row = text + (size_t)enc_rows[warp] * ld;
+    int out = cu[warp];
+    for (int c0 = 0; c0 < T; c0 += 32) {
+        const int c = c0 + lane;
+        const bool keep = c < T && row[T + c] != 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int k = out + __popc(bal & ((1u << lane) - 1u));
+            tok_ids[k] = row[c];
+            tok_pos[k] = c;
+        }
+        out += __popc(bal);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- gather / scatter
 template <typename TS, typename TD>
 __global__ void gather_rows_kernel(const TS* __restrict__ src, const int32_t* __restrict__ idx, TD* __restrict__ dst,
@@ -329,6 +367,25 @@ extern "C" int morec_gather_rows(const void* src, const int32_t* idx, void* dst,
     else if (src_dtype == 0 && dst_dtype == 1) gather_rows_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
     else if (src_dtype == 1 && dst_dtype == 1) gather_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
     else gather_rows_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, n, H, ld_src, ld_dst);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_mask_row_lens(const int64_t* text, int ld, int T, int n, int32_t* lens, void* stream) {
+    MOREC_CHECK_ARG(text && lens, "mask_row_lens: null pointer");
+    MOREC_CHECK_ARG(T > 0 && ld >= 2 * T, "mask_row_lens: rows must hold T ids followed by T mask entries");
+    if (n <= 0) return MOREC_OK;
+    mask_row_lens_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(text, ld, T, n, lens);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_pack_tokens(const int64_t* text, int ld, int T, const int32_t* enc_rows, const int32_t* cu,
+                                 int n_enc, int64_t* tok_ids, int32_t* tok_pos, void* stream) {
+    MOREC_CHECK_ARG(text && enc_rows && cu && tok_ids && tok_pos, "pack_tokens: null pointer");
+    MOREC_CHECK_ARG(T > 0 && ld >= 2 * T, "pack_tokens: rows must hold T ids followed by T mask entries");
+    if (n_enc <= 0) return MOREC_OK;
+    pack_tokens_kernel<<<(n_enc + 7) / 8, 256, 0, (cudaStream_t)stream>>>(text, ld, T, enc_rows, cu, n_enc, tok_ids, tok_pos);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

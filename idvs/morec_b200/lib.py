@@ -53,6 +53,8 @@ def load():
         "morec_cast_f32_to_bf16": [P, P, L, P],
         "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
         "morec_clock_probe": [P, P],
+        "morec_mask_row_lens": [P, I, I, I, P, P],
+        "morec_pack_tokens": [P, I, I, P, P, I, P, P, P],
         "morec_attn_gen_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, I, F, U, U, P],
         "morec_attn_gen_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, I, F, U, U, P],
         "morec_scale_add_rows": [P, P, P, P, I, F, P, I, I, I, I, P],
@@ -222,8 +224,9 @@ def h2d(arr, device):
 _D2H_BUF = {}
 
 
-def d2h_many(tensors):
-    """several small device tensors -> numpy arrays with ONE stream synchronisation"""
+def d2h_begin(tensors):
+    """enqueue the device->host copies of several small tensors (pinned buffers) and record an event; the caller can
+    keep issuing independent work and collects the arrays with d2h_end (ONE host wait for all of them)"""
     outs = []
     for i, t in enumerate(tensors):
         t = t.contiguous()
@@ -234,8 +237,20 @@ def d2h_many(tensors):
             _D2H_BUF[key] = buf
         buf.copy_(t.reshape(-1), non_blocking=True)
         outs.append((buf, t.shape))
-    torch.cuda.current_stream().synchronize()
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev, outs
+
+
+def d2h_end(handle):
+    ev, outs = handle
+    ev.synchronize()
     return [b.numpy().reshape(sh).copy() for b, sh in outs]
+
+
+def d2h_many(tensors):
+    """several small device tensors -> numpy arrays with ONE stream synchronisation"""
+    return d2h_end(d2h_begin(tensors))
 
 
 # enum mirrors
@@ -476,6 +491,27 @@ def scatter_add_rows(src, idx, dst):
                                        dst.stride(0), dtype_code(src), _stream())
     _check(rc, "morec_scatter_add_rows")
     return dst
+
+
+def mask_row_lens(text, T):
+    """text [n, >=2T] int64 (ids || attention mask), row stride arbitrary -> int32 [n] count of real tokens per row"""
+    assert text.dtype == torch.int64 and text.stride(1) == 1
+    n = text.shape[0]
+    lens = torch.empty(n, device=text.device, dtype=torch.int32)
+    rc = load().morec_mask_row_lens(_ptr(text), text.stride(0), T, n, _ptr(lens), _stream())
+    _check(rc, "morec_mask_row_lens")
+    return lens
+
+
+def pack_tokens(text, T, enc_rows, cu, n_tok):
+    """kept word pieces of the rows enc_rows (int32) of text -> (tok_ids int64 [n_tok], tok_pos int32 [n_tok])"""
+    assert text.dtype == torch.int64 and text.stride(1) == 1
+    tok_ids = torch.empty(n_tok, device=text.device, dtype=torch.int64)
+    tok_pos = torch.empty(n_tok, device=text.device, dtype=torch.int32)
+    rc = load().morec_pack_tokens(_ptr(text), text.stride(0), T, _ptr(enc_rows), _ptr(cu), enc_rows.numel(),
+                                  _ptr(tok_ids), _ptr(tok_pos), _stream())
+    _check(rc, "morec_pack_tokens")
+    return tok_ids, tok_pos
 
 
 def colsum(x, out):

@@ -104,37 +104,53 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         ps += [self.fc.weight, self.fc.bias]
         return ps
 
-    def forward(self, text, am_host=None):
+    def prepare(self):
+        """batch-independent per-forward state (flat parameter list, fused QKV buffers, compute-dtype weights); issued
+        before the packing plan's host sync so it overlaps the tail of the previous step"""
+        flat = self._flat_params()
+        wqkv, bqkv = self._fused_qkv()
+        return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=ops.prepare_tower_weights(wqkv, flat, _adt(self)))
+
+    def forward(self, text, lens_host=None, prep=None):
         """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0.
-        am_host: optional host copy (numpy bool [n, T]) of the attention mask when the caller already fetched it."""
+        lens_host: optional host copy (numpy int [n]) of the real-token count per row when the caller already fetched
+        it; prep: result of prepare() when the caller already issued it."""
         n, two_t = text.shape
         T = two_t // 2
         cfg = self.bert_model.config
         adt = _adt(self)
         D = self.fc.weight.shape[0]
         dev = text.device
-        # ---- packing plan: ONE device->host round trip (the attention mask, n*T bytes), index arithmetic in numpy
-        am = am_host if am_host is not None else lib.d2h_many([text[:, T:] != 0])[0]   # size-determining sync
-        lens = am.sum(axis=1)
-        enc_rows = np.nonzero(lens > 0)[0]
+        if text.dtype != torch.int64 or text.stride(1) != 1:
+            text = text.to(torch.int64).contiguous()
+        # ---- packing plan: ONE device->host round trip (n token counts), prefix sum in numpy, token placement on device
+        if lens_host is None:
+            h = lib.d2h_begin([lib.mask_row_lens(text, T)])         # size-determining sync ...
+            if prep is None:
+                prep = self.prepare()                               # ... with the weight casts issued behind the copy
+            lens = lib.d2h_end(h)[0]
+        else:
+            lens = lens_host
+            if prep is None:
+                prep = self.prepare()
+        enc_rows = np.flatnonzero(lens > 0).astype(np.int32)
         n_enc = int(enc_rows.size)
         if n_enc == 0:
             return torch.zeros(n, D, device=dev, dtype=adt)
-        r, c = np.nonzero(am[enc_rows])                             # row-major: tokens of one item stay contiguous
-        src = enc_rows[r].astype(np.int64) * two_t + c              # flat index of every kept word piece in `text`
-        cu_np = np.zeros(n_enc + 1, dtype=np.int32)
-        np.cumsum(lens[enc_rows], out=cu_np[1:])
-        plan = lib.h2d(np.concatenate([src, c.astype(np.int64), cu_np.astype(np.int64)]), dev)
-        n_tok = int(src.size)
-        tok_ids = text.reshape(-1)[plan[:n_tok]].to(torch.int64).contiguous()
-        tok_pos = plan[n_tok:2 * n_tok].to(torch.int32)
-        cu = plan[2 * n_tok:].to(torch.int32)
-        cls_rows = cu[:-1].contiguous()
+        plan_np = np.empty(2 * n_enc + 1, dtype=np.int32)
+        plan_np[:n_enc] = enc_rows
+        plan_np[n_enc] = 0
+        np.cumsum(lens[enc_rows], out=plan_np[n_enc + 1:])
+        n_tok = int(plan_np[-1])
+        plan = lib.h2d(plan_np, dev)
+        cu = plan[n_enc:]
+        tok_ids, tok_pos = lib.pack_tokens(text, T, plan[:n_enc], cu, n_tok)
+        cls_rows = cu[:-1]
         drop = _drop_ctx(self.training, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
         meta = dict(n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps, max_len=T,
                     adt=adt, drop=drop, x3=_x3(self))
-        meta["wqkv"], meta["bqkv"] = self._fused_qkv()
-        E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *self._flat_params())
+        meta["wqkv"], meta["bqkv"], meta["cw"] = prep["wqkv"], prep["bqkv"], prep["cw"]
+        E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *prep["flat"])
         if n_enc == n:
             return E
         s2e = np.full(n, -1, dtype=np.int32)
@@ -159,9 +175,9 @@ class Bert_Encoder(torch.nn.Module):                # reference: encoders.py:73-
         self.text_encoders = nn.ModuleDict({'title': Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
         self.newsname = [name for name in set(args.news_attributes) & {'title', 'abstract', 'body'}]
 
-    def forward(self, news, am_host=None):
+    def forward(self, news, lens_host=None, prep=None):
         vecs = [self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]),
-                                            am_host if len(self.newsname) == 1 else None)
+                                            lens_host if len(self.newsname) == 1 else None, prep)
                 for name in self.newsname]
         if len(vecs) == 1:
             return vecs[0]

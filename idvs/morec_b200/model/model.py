@@ -74,19 +74,21 @@ class Model(torch.nn.Module):
         cfg = te.text_encoders['title'].bert_model.config
         dropout_on = self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
         if self.item_dedup == "always" or (self.item_dedup == "auto" and not dropout_on):
-            # distinct non-pad ids -> first slot holding each.  One device->host fetch (ids + attention masks, one
-            # stream sync) feeds both this index arithmetic and the token-packing plan of the text tower.
+            # distinct non-pad ids -> first slot holding each.  One device->host fetch (ids + per-slot token counts, one
+            # host wait) feeds both this index arithmetic and the token-packing plan of the text tower.
             T = self.args.num_words_title
             single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
-            if single:
-                ids_np, am_np = lib.d2h_many([ids_flat, sample_items[:, T:2 * T] != 0])
-            else:
-                ids_np, am_np = lib.d2h_many([ids_flat])[0], None
+            if single and (sample_items.dtype != torch.int64 or sample_items.stride(1) != 1):
+                sample_items = sample_items.to(torch.int64).contiguous()
+            h = lib.d2h_begin([ids_flat, lib.mask_row_lens(sample_items, T)] if single else [ids_flat])
+            prep = te.text_encoders['title'].prepare() if single else None   # weight casts behind the copy, before the wait
+            got = lib.d2h_end(h)
+            ids_np, lens_np = (got[0], got[1]) if single else (got[0], None)
             nz = np.nonzero(ids_np)[0]
             _, first, inv = np.unique(ids_np[nz], return_index=True, return_inverse=True)
             dev = ids_flat.device
             rows = nz[first]
-            E_u = te(sample_items[lib.h2d(rows, dev)], am_np[rows] if am_np is not None else None)
+            E_u = te(sample_items[lib.h2d(rows, dev)], lens_np[rows] if lens_np is not None else None, prep)
             s2u = np.full(ids_np.size, -1, dtype=np.int32)
             s2u[nz] = inv.astype(np.int32)
             return ops.GatherRowsFn.apply(E_u, lib.h2d(s2u, dev), E_u.dtype)

@@ -198,6 +198,18 @@ def _layer_struct(meta, l, n_tok, n_seq, H, I, cu, w, small, acts, tmp_h):
 
 
 
+def prepare_tower_weights(wqkv_bufs, flat_params, adt):
+    """compute-dtype copies of every GEMM weight of the text tower (bf16 mode: 4 casts per layer + fc).  They do not
+    depend on the batch, so the caller issues them BEFORE it waits for the packing plan's device->host copy: the casts
+    then run while the host computes the plan instead of sitting between the sync and the first layer."""
+    n_layers = (len(flat_params) - 7) // 16
+    layers = []
+    for l in range(n_layers):
+        ps = flat_params[5 + 16 * l: 5 + 16 * (l + 1)]
+        layers.append((_cw(wqkv_bufs[l], adt), _cw(ps[6], adt), _cw(ps[10], adt), _cw(ps[12], adt)))
+    return dict(layers=layers, fc=_cw(flat_params[-2], adt))
+
+
 class BertTowerFn(torch.autograd.Function):
     """E[n_seq, D] = GELU(fc(BERT(tokens)[CLS])) over PACKED tokens (pad tokens and pad items are never computed).
 
@@ -235,12 +247,17 @@ class BertTowerFn(torch.autograd.Function):
         emb_saved = (x_pre if x_pre is not None else x, rstd0)
         del z
         layers = []
+        cw = meta.get("cw")                     # weights already in the compute dtype (prepare_tower_weights)
         use_seq = not lib._GEMM_TIMING          # C++ layer sequencer; the per-kernel path is kept for the roofline leg
         tmp_h = new((n_tok, H)) if use_seq else None
         for l in range(n_layers):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
-            wqkv, bqkv = _cw(meta["wqkv"][l], adt), meta["bqkv"][l]      # fused [3H, H] / [3H] (FusedParamGroup)
-            w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
+            bqkv = meta["bqkv"][l]                                       # fused [3H] (FusedParamGroup)
+            if cw is not None:
+                wqkv, w_ao, w_i, w_o = cw["layers"][l]
+            else:
+                wqkv = _cw(meta["wqkv"][l], adt)                         # fused [3H, H]
+                w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
             I = iw.shape[0]
             if use_seq:
                 qkv, ctxo, x1, x2 = new((n_tok, 3 * H)), new((n_tok, H)), new((n_tok, H)), new((n_tok, H))
@@ -274,7 +291,7 @@ class BertTowerFn(torch.autograd.Function):
         cls = lib.gather_rows(x, cls_rows)                                # [n_seq, H]
         D = fc_w.shape[0]
         fc_pre = torch.empty(n_seq, D, device=dev, dtype=adt)
-        w_fc = _cw(fc_w, adt)
+        w_fc = cw["fc"] if cw is not None else _cw(fc_w, adt)
         E = lib.linear_fwd(cls, w_fc, fc_b.detach(), epilogue=lib.EPI_GELU, pre=fc_pre)
         ctx.meta = meta
         ctx.own_ws = own_ws

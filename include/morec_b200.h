@@ -155,6 +155,13 @@ int morec_gather_rows(const void* src, const int32_t* idx, void* dst, int n, int
 int morec_scatter_add_rows(const void* src, const int32_t* idx, float* dst, int n, int H, int ld_src, int ld_dst,
                            int src_dtype, void* stream);
 int morec_colsum(const void* x, float* out, int M, int N, int ld, int dtype, void* stream);
+/* Token packing plan of the text tower (encoders.py:107-117 feeds [n, 2T] rows: T word-piece ids || T attention-mask
+ * entries, run.py:93-98).  mask_row_lens: lens[r] = #(mask entries != 0) of row r -- the only per-item number the host
+ * needs (prefix sum -> cu_seqlens).  pack_tokens: for encoded item s (row enc_rows[s]) the kept word pieces, in column
+ * order, are written to tok_ids / tok_pos [cu[s], cu[s+1]) (tok_pos = original column). */
+int morec_mask_row_lens(const int64_t* text, int ld, int T, int n, int32_t* lens, void* stream);
+int morec_pack_tokens(const int64_t* text, int ld, int T, const int32_t* enc_rows, const int32_t* cu, int n_enc,
+                      int64_t* tok_ids, int32_t* tok_pos, void* stream);
 /* out[r] = (x ? x[r] : 0) + alpha * (group_scale ? group_scale[r / rows_per_group] : 1) * y[idx ? idx[r] : r]
  * (residual add of a window-permuted branch with per-image drop-path scale: HF SwinLayer.forward; its backward;
  * broadcast backward of the mean pool).  idx[r] < 0 contributes 0. */

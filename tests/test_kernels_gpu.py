@@ -583,3 +583,27 @@ def test_attention_tc_dropout_mask_and_grads(lib, dt, dh, L):
     with lib.fp32_mode(False):
         bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], do, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], **kw)
     assert rel(dqkv, qd.grad) < 2 * tol
+
+
+def test_token_packing_plan(lib):
+    """device-side packing plan == the numpy index arithmetic it replaces (bit-exact, arbitrary masks, strided rows)"""
+    import numpy as np
+    torch.manual_seed(12)
+    n, T, extra = 37, 30, 7
+    ids = torch.randint(1, 30000, (n, T))
+    mask = (torch.rand(n, T) > 0.4).long()
+    mask[3] = 0                                   # pad item
+    mask[5] = 1                                   # full row
+    mask[8, :] = 0; mask[8, -1] = 1               # single late token
+    wide = torch.cat([ids, mask, torch.full((n, extra), -5)], 1).cuda()          # row stride 2T + extra
+    text = wide[:, :2 * T]
+    lens = lib.mask_row_lens(text, T)
+    assert torch.equal(lens.cpu(), mask.sum(1).to(torch.int32))
+    am = mask.numpy() != 0
+    enc = np.flatnonzero(am.sum(1) > 0).astype(np.int32)
+    cu = np.zeros(enc.size + 1, dtype=np.int32)
+    np.cumsum(am.sum(1)[enc], out=cu[1:])
+    tok_ids, tok_pos = lib.pack_tokens(text, T, torch.from_numpy(enc).cuda(), torch.from_numpy(cu).cuda(), int(cu[-1]))
+    r, c = np.nonzero(am[enc])
+    assert torch.equal(tok_ids.cpu(), ids[torch.from_numpy(enc[r]).long(), torch.from_numpy(c)])
+    assert torch.equal(tok_pos.cpu(), torch.from_numpy(c.astype(np.int32)))
