@@ -150,6 +150,7 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         meta = dict(n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps, max_len=T,
                     adt=adt, drop=drop, x3=_x3(self))
         meta["wqkv"], meta["bqkv"], meta["cw"] = prep["wqkv"], prep["bqkv"], prep["cw"]
+        meta["grad_sync"] = getattr(self, "overlap_grad_sync", False)
         E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *prep["flat"])
         if n_enc == n:
             return E

@@ -56,6 +56,22 @@ class Model(torch.nn.Module):
         self.parallel_mode = getattr(args, "parallel_mode", "local")
         self.compute_dtype = getattr(args, "compute_dtype", "fp32")
         self.set_compute_dtype(self.compute_dtype)
+        # Multi-GPU: the text tower averages its own gradients, layer by layer, overlapped with its backward
+        # (ops._GradSync); DistributedDataParallel (run.py:148) is told to leave those parameters alone (see the
+        # `_ddp_params_and_buffers_to_ignore` property).  Everything else (SASRec, ID embedding) stays with DDP.
+        self._overlap_grad_sync = bool(self.use_modal and getattr(args, "overlap_grad_sync", True))
+        self._ddp_wrapped = False
+
+    @property
+    def _ddp_params_and_buffers_to_ignore(self):
+        """Read by DistributedDataParallel's constructor (and by nothing else): the text tower's parameters are
+        excluded from DDP's reducer because the tower all-reduces them itself during its backward.  The read also
+        records that this replica IS wrapped by DDP -- a bare Model in a process that merely has torch.distributed
+        initialised must not start collectives of its own."""
+        if not self._overlap_grad_sync:
+            return []
+        self._ddp_wrapped = True
+        return [n for n, _ in self.named_parameters() if n.startswith("bert_encoder.")]
 
     def set_compute_dtype(self, name):
         assert name in ("fp32", "tf32", "bf16")
@@ -71,6 +87,7 @@ class Model(torch.nn.Module):
         if not self.use_modal:
             return self.id_embedding(sample_items.reshape(-1))
         te = self.bert_encoder
+        te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and self._ddp_wrapped
         cfg = te.text_encoders['title'].bert_model.config
         dropout_on = self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
         if self.item_dedup == "always" or (self.item_dedup == "auto" and not dropout_on):
@@ -144,10 +161,23 @@ class Model(torch.nn.Module):
         ids_all = par.all_gather_small(ids_flat).reshape(-1)                      # [G*C]
         if self.use_modal:
             items_all = par.all_gather_small(sample_items.contiguous()).reshape(G * C, -1)
-            plan = par.plan_global_batch(lib.d2h_many([ids_all])[0], G, rank)     # host index arithmetic (one D2H)
+            te = self.bert_encoder
+            te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and self._ddp_wrapped
+            T = self.args.num_words_title
+            single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
+            if single and items_all.dtype != torch.int64:
+                items_all = items_all.to(torch.int64)
+            # ONE host wait: ids + per-slot token counts; the weight casts are issued behind the copies
+            h = lib.d2h_begin([ids_all, lib.mask_row_lens(items_all, T)] if single else [ids_all])
+            prep = te.text_encoders['title'].prepare() if single else None
+            got = lib.d2h_end(h)
+            plan = par.plan_global_batch(got[0], G, rank)                         # host index arithmetic
             n_mine = int(plan.my_first_slots.size)
             my_items = items_all[lib.h2d(plan.my_first_slots, dev)]
-            E_mine = self.bert_encoder(my_items) if n_mine > 0 else torch.zeros(0, D, device=dev, dtype=adt)
+            if n_mine > 0:
+                E_mine = te(my_items, got[1][plan.my_first_slots] if single else None, prep)
+            else:
+                E_mine = torch.zeros(0, D, device=dev, dtype=adt)
             pad_idx = np.full(plan.u_max, -1, dtype=np.int32)
             pad_idx[:n_mine] = np.arange(n_mine, dtype=np.int32)
             if n_mine > 0:
