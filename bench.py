@@ -424,7 +424,7 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "morec::gemm_kernel (tcgen05, all fwd/dgrad/wgrad/scoring launches)",
+    roofline = {"bound": "tensor", "kernel": "morec::gemm2_kernel / gemm_kernel (tcgen05 CTA-pair and single-CTA GEMMs: every fwd / dgrad / wgrad / scoring launch)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                 "peak_source": peak_src, "launches_timed": gemm_n, "gemm_ms_per_step": gemm_ms / K,
                 "note": {"fp32": "3xTF32 parity mode: 3 tensor-core passes per algorithmic FLOP and kind::tf32 runs at half "
@@ -440,8 +440,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "mode": args.mode,
                        "parallelism": f"dp{world}" + (f" ({args.parallel}: " + ("item embeddings all-gathered, global negatives, "
-                                      "reduce-scatter in backward + DDP grad all-reduce)" if args.parallel == "global"
-                                      else "reference DDP, rank-local negatives)") if world > 1 else ""),
+                                      "reduce-scatter in backward; text-tower gradients all-reduced layer by layer inside its backward, the rest by DDP)" if args.parallel == "global"
+                                      else "reference DDP semantics, rank-local negatives; text-tower gradients all-reduced layer by layer inside its backward)") if world > 1 else ""),
                        "l2_policy": "every step uses a different batch and streams >10 GB of activations (>> 126 MB L2)",
                        "dropout": cfg["drop"], "optimizer": "FusedAdamW (2 groups)",
                        "items_encoded": "each distinct non-pad item of the (global) batch once; pad tokens skipped"},

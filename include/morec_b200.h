@@ -16,7 +16,10 @@
  *            1 = bf16 storage, tcgen05 kind::f16, fp32 accumulate                                   ("bf16")
  *            2 = fp32 storage, error-compensated 3xTF32 on tcgen05 (hi*hi + hi*lo + lo*hi, operands split in
  *                shared memory), fp32-grade results: the PARITY mode checked against the CPU oracle  ("fp32")
- *     element-wise / attention / LayerNorm kernels only distinguish the storage type (0 or 2 = fp32, 1 = bf16).
+ *     element-wise / LayerNorm kernels only distinguish the storage type (0 or 2 = fp32, 1 = bf16).  The attention
+ *     entry points take the same three codes: 2 runs the exact-fp32 SIMT kernels (parity mode), 0 / 1 run the
+ *     tensor-core kernels (TF32 resp. bf16 mma, fp32 softmax) when the shape is covered (<= 64 tokens with 32- or
+ *     64-wide heads, <= 32 tokens with 256-wide heads) and fall back to the SIMT kernels otherwise.
  */
 #ifndef MOREC_B200_H
 #define MOREC_B200_H
