@@ -5,7 +5,7 @@ import re
 import sys
 
 path = sys.argv[1]
-lines = [l for l in open(path) if not l.startswith("==")]
+lines = [l for l in open(path) if not l.startswith("==") and not l.startswith("#")]
 agg = collections.defaultdict(lambda: [0, 0.0])
 tot = 0.0
 for row in csv.DictReader(lines):
