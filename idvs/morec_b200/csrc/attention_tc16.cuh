@@ -305,11 +305,19 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
     dim3 grid(gx, p.n_heads);
     if (!bwd) {
         auto kern = attn_tc16_fwd_kernel<D, LP>;
-        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t set_f = 0;                         // per instantiation: raise the opt-in limit only when it grows
+        if (smem > set_f) {
+            MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_f = smem;
+        }
         kern<<<grid, C::THREADS, smem, stream>>>(p);
     } else {
         auto kern = attn_tc16_bwd_kernel<D, LP>;
-        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t set_b = 0;
+        if (smem > set_b) {
+            MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_b = smem;
+        }
         kern<<<grid, C::THREADS, smem, stream>>>(p);
     }
     MOREC_LAUNCH_CHECK();

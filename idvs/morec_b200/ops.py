@@ -105,7 +105,12 @@ class _GradSync:
         import torch.distributed as dist
         end = self.arena.off
         if end > self.start:
-            self.handles.append(dist.all_reduce(self.arena.buf[self.start:end], op=dist.ReduceOp.AVG, async_op=True))
+            t = self.arena.buf[self.start:end]
+            if dist.get_backend() == "gloo":              # CPU tests: no AVG / no stream overlap on gloo
+                dist.all_reduce(t)
+                t.div_(dist.get_world_size())
+            else:
+                self.handles.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True))
             self.start = end
 
     def wait(self):

@@ -130,3 +130,65 @@ def test_global_mode_equals_single_process_oracle_world2():
         assert p.exitcode == 0
     for rank, ok, a, b in res:
         assert ok, (rank, a, b)
+
+
+def _gradsync_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from idvs.morec_b200 import ops
+        shapes = [(7, 3), (5,), (4, 4), (9,), (2, 6)]
+        arena = ops._Arena(torch.device("cpu"), shapes)
+        assert ops._GradSync.enabled({"grad_sync": True}) and not ops._GradSync.enabled({})
+        sync = ops._GradSync(arena)
+        vals = []
+        for i, sh in enumerate(shapes):                 # "layers": take a slice, fill it, flush after every second one
+            g = arena.take(sh)
+            g.copy_(torch.full(sh, float((rank + 1) * (i + 1))))
+            vals.append(g)
+            if i % 2 == 1:
+                sync.flush()
+        sync.wait()                                      # flushes the tail
+        ok = all(torch.allclose(g, torch.full_like(g, (i + 1) * (1 + world) / 2.0)) for i, g in enumerate(vals))
+        sync.wait()                                      # idempotent: nothing left to reduce
+        ok = ok and all(torch.allclose(g, torch.full_like(g, (i + 1) * (1 + world) / 2.0)) for i, g in enumerate(vals))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_layerwise_gradient_sync_world2():
+    """ops._GradSync: slices of the gradient arena are averaged over ranks exactly once, in flush order"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gradsync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_ddp_ignore_list_marks_wrapping():
+    """Model._ddp_params_and_buffers_to_ignore: DDP skips the text tower and the read marks the replica as wrapped"""
+    import types
+    from transformers import BertConfig, BertModel
+    from idvs.morec_b200.model import Model
+    cfg = BertConfig(hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64, vocab_size=100,
+                     max_position_embeddings=16)
+    a = types.SimpleNamespace(max_seq_len=4, embedding_dim=16, num_attention_heads=2, drop_rate=0.0, transformer_block=1,
+                              num_words_title=8, num_words_abstract=0, num_words_body=0, news_attributes=["title"],
+                              bert_model_load="bert_tiny", word_embedding_dim=32)
+    m = Model(a, 10, True, BertModel(cfg), np.ones(11) / 11)
+    assert m._ddp_wrapped is False
+    names = m._ddp_params_and_buffers_to_ignore
+    assert m._ddp_wrapped is True
+    all_names = [n for n, _ in m.named_parameters()]
+    assert names and all(n in all_names and n.startswith("bert_encoder.") for n in names)
+    assert not any(n.startswith("user_encoder.") for n in names)
+    assert "_ddp_params_and_buffers_to_ignore" not in m.state_dict()
+    m_id = Model(a, 10, False, None, np.ones(11) / 11)          # ID tower: nothing to ignore, never marked
+    assert m_id._ddp_params_and_buffers_to_ignore == [] and m_id._ddp_wrapped is False
