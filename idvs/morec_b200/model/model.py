@@ -102,7 +102,8 @@ class Model(torch.nn.Module):
             got = lib.d2h_end(h)
             ids_np, lens_np = (got[0], got[1]) if single else (got[0], None)
             nz = np.nonzero(ids_np)[0]
-            _, first, inv = np.unique(ids_np[nz], return_index=True, return_inverse=True)
+            from ..parallel import unique_first
+            _, first, inv = unique_first(ids_np[nz])
             dev = ids_flat.device
             rows = nz[first]
             E_u = te(sample_items[lib.h2d(rows, dev)], lens_np[rows] if lens_np is not None else None, prep)

@@ -44,6 +44,26 @@ class GlobalPlan:
     slot_to_row: np.ndarray    # [G*C] row of the gathered table [G*u_max, D] for every global slot (-1 = pad slot)
 
 
+def unique_first(x: np.ndarray):
+    """(uniq, first, inv) == np.unique(x, return_index=True, return_inverse=True) for non-negative integer ids.
+    When the id range is comparable to the number of slots (the usual case: in-batch ids of a catalogue) a direct
+    table over the id range replaces np.unique's sort: O(n + max_id) instead of O(n log n) -- the global plan of an
+    8-GPU step (13,312 slots) sits between the size-determining sync and the first kernel launch, where the GPU idles."""
+    x = np.asarray(x)
+    n = x.size
+    if n == 0:
+        return x[:0], np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    hi = int(x.max())
+    if int(x.min()) < 0 or hi > 16 * n:                 # sparse id range: the sort is cheaper than touching the table
+        return np.unique(x, return_index=True, return_inverse=True)
+    first_of_id = np.full(hi + 1, -1, dtype=np.int64)
+    first_of_id[x[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)     # last write wins = smallest slot index
+    uniq = np.flatnonzero(first_of_id >= 0)
+    rank_of_id = np.empty(hi + 1, dtype=np.int64)
+    rank_of_id[uniq] = np.arange(uniq.size, dtype=np.int64)
+    return uniq.astype(x.dtype, copy=False), first_of_id[uniq], rank_of_id[x]
+
+
 def plan_global_batch(ids_all: np.ndarray, G: int, rank: int) -> GlobalPlan:
     """ids_all: int64 [G*C] item ids of every slot of the global batch (rank-major).  Deterministic, host-side,
     identical on every rank.  Unique non-pad items are sorted by id and dealt round-robin: item k -> rank k % G,
@@ -51,7 +71,7 @@ def plan_global_batch(ids_all: np.ndarray, G: int, rank: int) -> GlobalPlan:
     ids_all = np.asarray(ids_all, dtype=np.int64).reshape(-1)
     C = ids_all.size // G
     nz = ids_all != 0
-    uniq, first, inv = np.unique(ids_all[nz], return_index=True, return_inverse=True)
+    uniq, first, inv = unique_first(ids_all[nz])
     nz_slots = np.nonzero(nz)[0]
     first_slots = nz_slots[first]                         # global slot of the first occurrence of each unique item
     n_unique = int(uniq.size)

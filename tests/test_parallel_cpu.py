@@ -192,3 +192,14 @@ def test_ddp_ignore_list_marks_wrapping():
     assert "_ddp_params_and_buffers_to_ignore" not in m.state_dict()
     m_id = Model(a, 10, False, None, np.ones(11) / 11)          # ID tower: nothing to ignore, never marked
     assert m_id._ddp_params_and_buffers_to_ignore == [] and m_id._ddp_wrapped is False
+
+
+def test_unique_first_matches_numpy():
+    g = np.random.default_rng(3)
+    for n, hi in [(1, 5), (50, 7), (1664, 50000), (13312, 50000), (40, 10 ** 9)]:     # the last one takes the np.unique path
+        x = g.integers(1, hi + 1, size=n)
+        u0, f0, i0 = np.unique(x, return_index=True, return_inverse=True)
+        u1, f1, i1 = par.unique_first(x)
+        assert np.array_equal(u0, u1) and np.array_equal(f0, f1) and np.array_equal(i0, i1)
+    u, f, i = par.unique_first(np.zeros(0, dtype=np.int64))
+    assert u.size == 0 and f.size == 0 and i.size == 0
