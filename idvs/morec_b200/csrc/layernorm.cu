@@ -1,4 +1,5 @@
-// Fused (dropout ->) residual/position add -> LayerNorm (-> dropout) forward and backward, one warp per row.
+// Fused (dropout ->) residual/position add -> LayerNorm (-> dropout) forward (one warp per row) and backward (one
+// thread per float4 column, LN_R rows per block step).
 //
 // Replaces the eager sequences   LayerNorm(residual + dropout(x))            modules.py:16-17, 62-63; HF BertSelfOutput
 //                                dropout(LayerNorm(x + position_embedding))  modules.py:89-93; HF BertEmbeddings
@@ -291,7 +292,6 @@ extern "C" int morec_layernorm_bwd(const void* dy, const void* dy2, const void* 
     static int occ_f32[17] = {0}, occ_bf16[17] = {0};
     int& occ = (dtype == 1 ? occ_bf16 : occ_f32)[threads / 32];
     const bool big = threads > 256;
-#define LN_BWD_CALL(TT, BB, WHAT) WHAT(ln_bwd_kernel<TT, BB>)
     if (occ == 0) {
         cudaError_t e;
         if (dtype == 1) e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<__nv_bfloat16, true>, threads, 0)
@@ -301,7 +301,6 @@ extern "C" int morec_layernorm_bwd(const void* dy, const void* dy2, const void* 
         MOREC_CUDA(e);
         if (occ < 1) occ = 1;
     }
-#undef LN_BWD_CALL
     int blocks = (M + LN_R - 1) / LN_R;
     const int cap = num_sms() * occ;
     if (blocks > cap) blocks = cap;
