@@ -143,3 +143,25 @@ def test_vision_oracle_matches_reference():
             got = p[k].grad
         assert got is not None, k
         assert float((got - gref).abs().max()) <= 2e-4 * (float(gref.abs().max()) + 1e-12) + 1e-7, k
+
+
+def test_mask_closed_form_equals_loops_random():
+    """property test: the closed form of SURVEY.md Appendix A == the element-by-element re-derivation of
+    model.py:51-63 on random left-padded batches with heavy id collisions (small catalogues), B = 1 included"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 5), st.integers(2, 7), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
+    def check(B, L, N, seed):
+        g = torch.Generator().manual_seed(seed)
+        ids = torch.randint(1, N + 1, (B, L + 1), generator=g)
+        n_real = torch.randint(2, L + 2, (B,), generator=g)              # at least the target and one input
+        for b in range(B):
+            ids[b, : L + 1 - int(n_real[b])] = 0                         # left padding (dataset.py:24-36)
+        a, lo = O.reject_mask_closed_form(ids), O.reject_mask_loops(ids)
+        assert torch.equal(a, lo)
+        tgt = O.ce_labels(B, L)
+        v = O.valid_rows(O.log_mask_from_ids(ids))
+        assert not a[torch.arange(a.shape[0]), tgt][v].any()             # a valid row never masks its own target
+
+    check()
