@@ -225,6 +225,29 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bflo
         st4<__nv_bfloat16>(dst + 4 * i, *reinterpret_cast<const float4*>(src + 4 * i));
 }
 
+// many tensors in ONE launch (bf16 weight shadows of a whole tower: 49 casts for BERT-base): same chunk table as AdamW
+struct CastTensor {
+    const float* src; __nv_bfloat16* dst; long long n;
+};
+constexpr int CAST_CHUNK = 16384;
+__device__ __forceinline__ int find_tensor(const int* __restrict__ chunk_start, int n_tensors, int chunk);
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastTensor* __restrict__ tensors,
+                                                         const int* __restrict__ chunk_start, int n_tensors, int n_chunks) {
+    for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+        const int t = find_tensor(chunk_start, n_tensors, ci);
+        const CastTensor ch = tensors[t];
+        const long long e0 = (long long)(ci - chunk_start[t]) * CAST_CHUNK;
+        const long long e1 = min(ch.n, e0 + CAST_CHUNK);
+        for (long long i = e0 + threadIdx.x * 4; i < e1; i += blockDim.x * 4) {
+            if (i + 4 <= e1) {
+                st4<__nv_bfloat16>(ch.dst + i, *reinterpret_cast<const float4*>(ch.src + i));
+            } else {
+                for (long long k = i; k < e1; ++k) ch.dst[k] = __float2bfloat16(ch.src[k]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- AdamW (multi-tensor)
 // One entry per parameter tensor; CTAs walk fixed-size chunks and find their tensor by binary search in the
 // exclusive prefix sum of per-tensor chunk counts (chunk_start[n_tensors + 1]).
@@ -459,6 +482,19 @@ extern "C" int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vo
     MOREC_CHECK_ARG(n % 4 == 0, "cast: n %% 4 != 0");
     if (n <= 0) return MOREC_OK;
     cast_f32_to_bf16_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (size_t)n / 4);
+    MOREC_LAUNCH_CHECK();
+    return MOREC_OK;
+}
+
+extern "C" int morec_cast_chunk_elems(void) { return CAST_CHUNK; }
+
+extern "C" int morec_cast_f32_to_bf16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
+                                            void* stream) {
+    MOREC_CHECK_ARG(tensors && chunk_start, "cast_multi: null table");
+    static_assert(sizeof(CastTensor) == sizeof(MorecCastTensor), "ABI struct mismatch");
+    if (n_chunks <= 0 || n_tensors <= 0) return MOREC_OK;
+    const int grid = n_chunks < num_sms() * 8 ? n_chunks : num_sms() * 8;
+    cast_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const CastTensor*)tensors, chunk_start, n_tensors, n_chunks);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

@@ -51,6 +51,7 @@ def load():
         "morec_colsum": [P, P, I, I, I, I, P],
         "morec_act_bwd": [P, P, P, L, I, I, P],
         "morec_cast_f32_to_bf16": [P, P, L, P],
+        "morec_cast_f32_to_bf16_multi": [P, P, I, I, P],
         "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
         "morec_clock_probe": [P, P],
         "morec_mask_row_lens": [P, I, I, I, P, P],
@@ -491,6 +492,39 @@ def scatter_add_rows(src, idx, dst):
                                        dst.stride(0), dtype_code(src), _stream())
     _check(rc, "morec_scatter_add_rows")
     return dst
+
+
+class CastPlan:
+    """persistent bf16 shadows of a fixed set of fp32 tensors + the device table that casts all of them in one launch"""
+
+    def __init__(self, srcs):
+        import numpy as np
+        lib = load()
+        lib.morec_cast_chunk_elems.restype = c_int
+        chunk = lib.morec_cast_chunk_elems()
+        dev = srcs[0].device
+        self.key = tuple(t.data_ptr() for t in srcs)
+        self.dst = [torch.empty(t.shape, device=dev, dtype=torch.bfloat16) for t in srcs]
+        n = len(srcs)
+        rec = np.zeros(n, dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("n", "<i8")], align=True))
+        assert rec.itemsize == 24
+        for i, (a, b) in enumerate(zip(srcs, self.dst)):
+            assert a.dtype == torch.float32 and a.is_contiguous() and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+            rec[i] = (a.data_ptr(), b.data_ptr(), a.numel())
+        counts = (rec["n"] + chunk - 1) // chunk
+        start = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(counts, out=start[1:])
+        self.n, self.n_chunks = n, int(start[-1])
+        self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
+        self.start = torch.from_numpy(start).to(dev)
+
+    def matches(self, srcs):
+        return len(srcs) == self.n and all(t.data_ptr() == k for t, k in zip(srcs, self.key))
+
+    def run(self):
+        rc = load().morec_cast_f32_to_bf16_multi(_ptr(self.table), _ptr(self.start), self.n, self.n_chunks, _stream())
+        _check(rc, "morec_cast_f32_to_bf16_multi")
+        return self.dst
 
 
 def mask_row_lens(text, T):

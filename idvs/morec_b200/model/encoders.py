@@ -109,7 +109,9 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         before the packing plan's host sync so it overlaps the tail of the previous step"""
         flat = self._flat_params()
         wqkv, bqkv = self._fused_qkv()
-        return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=ops.prepare_tower_weights(wqkv, flat, _adt(self)))
+        if not hasattr(self, "_prep_cache"):
+            self._prep_cache = {}
+        return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=ops.prepare_tower_weights(wqkv, flat, _adt(self), self._prep_cache))
 
     def forward(self, text, lens_host=None, prep=None):
         """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0.

@@ -234,16 +234,29 @@ def _layer_struct(meta, l, n_tok, n_seq, H, I, cu, w, small, acts, tmp_h):
 
 
 
-def prepare_tower_weights(wqkv_bufs, flat_params, adt):
-    """compute-dtype copies of every GEMM weight of the text tower (bf16 mode: 4 casts per layer + fc).  They do not
-    depend on the batch, so the caller issues them BEFORE it waits for the packing plan's device->host copy: the casts
-    then run while the host computes the plan instead of sitting between the sync and the first layer."""
+def prepare_tower_weights(wqkv_bufs, flat_params, adt, cache=None):
+    """compute-dtype copies of every GEMM weight of the text tower (bf16 mode: 4 per layer + fc).  They do not depend
+    on the batch, so the caller issues them BEFORE it waits for the packing plan's device->host copy.  With a `cache`
+    dict the shadows are persistent buffers refreshed by ONE multi-tensor cast launch (lib.CastPlan) instead of 49
+    launches -- host time that an end-to-end step (loss read back every step) cannot hide.  The shadows of forward i
+    are overwritten by forward i+1, i.e. a backward must run before the weights change and the next forward starts
+    (every training loop does; re-casting unchanged weights writes identical values)."""
     n_layers = (len(flat_params) - 7) // 16
-    layers = []
+    srcs = []
     for l in range(n_layers):
         ps = flat_params[5 + 16 * l: 5 + 16 * (l + 1)]
-        layers.append((_cw(wqkv_bufs[l], adt), _cw(ps[6], adt), _cw(ps[10], adt), _cw(ps[12], adt)))
-    return dict(layers=layers, fc=_cw(flat_params[-2], adt))
+        srcs += [wqkv_bufs[l].detach(), ps[6].detach(), ps[10].detach(), ps[12].detach()]
+    srcs.append(flat_params[-2].detach())
+    if adt == torch.float32:
+        out = srcs
+    elif cache is not None and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in srcs):
+        plan = cache.get("cast_plan")
+        if plan is None or not plan.matches(srcs):
+            plan = cache["cast_plan"] = lib.CastPlan(srcs)
+        out = plan.run()
+    else:
+        out = [_cw(t, adt) for t in srcs]
+    return dict(layers=[tuple(out[4 * l: 4 * l + 4]) for l in range(n_layers)], fc=out[-1])
 
 
 class BertTowerFn(torch.autograd.Function):

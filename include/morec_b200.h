@@ -175,6 +175,17 @@ int morec_mean_rows(const void* x, void* out, int n_groups, int rows_per_group, 
 /* out = dy * act'(aux): mode 0 = erf-GELU with aux = pre-activation (encoders.py:70), 1 = ReLU with aux = output */
 int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mode, int dtype, void* stream);
 int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* the same for many tensors in ONE launch (the bf16 weight shadows of a whole tower): tensors = DEVICE array of
+ * n_tensors MorecCastTensor, chunk_start = DEVICE int32[n_tensors+1] exclusive prefix sum of
+ * ceil(n / morec_cast_chunk_elems()); src / dst 16-byte aligned. */
+typedef struct MorecCastTensor {
+    const float* src;
+    void* dst;
+    long long n;
+} MorecCastTensor;
+int morec_cast_chunk_elems(void);
+int morec_cast_f32_to_bf16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
+                                 void* stream);
 
 /* ---- multi-tensor AdamW with fused unscale + found-inf (run.py:159-162, 245-247) ---------------
  * tensors: DEVICE array of n_tensors MorecAdamTensor (one per parameter); chunk_start: DEVICE int32[n_tensors+1],

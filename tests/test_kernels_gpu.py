@@ -607,3 +607,17 @@ def test_token_packing_plan(lib):
     r, c = np.nonzero(am[enc])
     assert torch.equal(tok_ids.cpu(), ids[torch.from_numpy(enc[r]).long(), torch.from_numpy(c)])
     assert torch.equal(tok_pos.cpu(), torch.from_numpy(c.astype(np.int32)))
+
+
+def test_cast_multi_matches_elementwise_cast(lib):
+    """one-launch multi-tensor fp32 -> bf16 cast (tower weight shadows) == torch's cast, incl. ragged tails"""
+    torch.manual_seed(21)
+    srcs = [torch.randn(s, device="cuda") for s in [(2304, 768), (768,), (3, 5), (16385,), (64, 3072), (1,)]]
+    plan = lib.CastPlan(srcs)
+    assert plan.matches(srcs) and not plan.matches(srcs[:-1])
+    for rep in range(2):                                   # persistent shadows are refreshed in place
+        outs = plan.run()
+        for a, b in zip(srcs, outs):
+            assert b.dtype == torch.bfloat16 and b.shape == a.shape and torch.equal(b, a.to(torch.bfloat16))
+        for a in srcs:
+            a.mul_(1.5)
