@@ -107,10 +107,16 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
     def prepare(self):
         """batch-independent per-forward state (flat parameter list, fused QKV buffers, compute-dtype weights); issued
         before the packing plan's host sync so it overlaps the tail of the previous step"""
-        flat = self._flat_params()
-        wqkv, bqkv = self._fused_qkv()
         if not hasattr(self, "_prep_cache"):
             self._prep_cache = {}
+        c = self._prep_cache
+        bm = self.bert_model
+        key = (id(bm), len(bm.encoder.layer), id(bm.embeddings.word_embeddings.weight), id(self.fc.weight),
+               id(bm.encoder.layer[-1].output.dense.weight))
+        if c.get("flat_key") != key:                    # the ~200 Parameter OBJECTS only change under module surgery
+            c["flat"], c["flat_key"] = self._flat_params(), key
+        flat = c["flat"]
+        wqkv, bqkv = self._fused_qkv()                  # re-validated every call (.to() re-allocates parameters)
         return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=ops.prepare_tower_weights(wqkv, flat, _adt(self), self._prep_cache))
 
     def forward(self, text, lens_host=None, prep=None):

@@ -174,17 +174,18 @@ class FusedParamGroup:
 
     def __init__(self, params):
         self.params = list(params)
+        self._numels = [p.numel() for p in self.params]
         self.buf = None
 
     def _valid(self):
         if self.buf is None:
             return False
-        off = 0
-        base = self.buf.data_ptr()
-        for p in self.params:
-            if p.data_ptr() != base + 4 * off or p.device != self.buf.device:
+        # device pointers are unique across devices (unified addressing), so matching addresses imply the same device
+        ptr = self.buf.data_ptr()
+        for p, n in zip(self.params, self._numels):
+            if p.data_ptr() != ptr:
                 return False
-            off += p.numel()
+            ptr += 4 * n
         return True
 
     @torch.no_grad()
