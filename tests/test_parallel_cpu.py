@@ -117,14 +117,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_global_mode_equals_single_process_oracle_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_global_mode_equals_single_process_oracle(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
