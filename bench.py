@@ -180,7 +180,112 @@ def time_cpu_oracle(cfg, B_sample, steps, warmup, seed=12345):
     return dict(value=B_sample / dt, unit="sequences/s", cores=cores, kind="port",
                 sample=f"oracle port (plain PyTorch CPU fp32, oracle/morec_oracle.py), B={B_sample} of {cfg['B']} users "
                        f"per step (same L/T/D/encoder), {steps} timed step(s) after thread-count calibration "
-                       f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt
+                       f"(best of {os.cpu_count()} host cores: {cores} threads), {dt:.2f} s/step"), dt, steps
+
+
+# ------------------------------------------------------------------------------------------------ unmodified reference arm
+def ref_root():
+    """directory holding the UNMODIFIED reference `model/` packages: baseline/_ref (a git-ignored copy made by
+    __graft_entry__.build() in the authoring container; it travels to the GPU box with the gpurun snapshot), else
+    /root/reference when this runs in the authoring container itself."""
+    for r in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(r, "inbatch_sasrec_e2e_text", "model", "model.py")):
+            return r
+    return None
+
+
+def load_reference_model_cls(root, pkg="inbatch_sasrec_e2e_text"):
+    """import <root>/<pkg>/model as a uniquely named package (its own relative imports resolve inside it; nothing of
+    this repo is on that path) and return the reference's Model class"""
+    import importlib.util
+    name = "_ref_" + pkg + "_model"
+    if name in sys.modules:
+        return sys.modules[name].Model
+    d = os.path.join(root, pkg, "model")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod.Model
+
+
+def reference_step_fn(cfg, B, seed, root):
+    """one training step of the unmodified reference Model on CPU fp32 exactly as BASELINE.md §2 prescribes:
+    zero_grad -> forward(local_rank='cpu') -> backward -> AdamW (two groups, run.py:150-162), same synthetic batch
+    generator and same BERT-base config as the B200 arm"""
+    import torch
+    from transformers import BertConfig, BertModel
+    from idvs.morec_b200.synth import synth_batch
+    RefModel = load_reference_model_cls(root)
+    torch.manual_seed(seed)
+    bert = BertModel(BertConfig(**BERT_BASE))
+    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
+        if i in (197, 198):
+            p.requires_grad = False
+    batch = synth_batch(B, cfg["L"], cfg["N"], cfg["T"], seed, modal=True)
+    model = RefModel(make_args(cfg), cfg["N"], True, bert, batch["pop_prob"].numpy())
+    model.train()
+    bert_p = [p for n, p in model.named_parameters() if p.requires_grad and "bert_model" in n]
+    rec_p = [p for n, p in model.named_parameters() if p.requires_grad and "bert_model" not in n]
+    opt = torch.optim.AdamW([{"params": bert_p, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
+                             {"params": rec_p, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+    ids, items, lm = batch["ids"].reshape(-1), batch["items"], batch["log_mask"]
+
+    def step():
+        opt.zero_grad()
+        loss = model(ids, items, lm, "cpu")
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def time_reference(cfg, steps, warmup, budget_s, seed=12345, users=0):
+    """unmodified reference at the FULL batch (B = cfg['B']).  A BERT-base CPU step takes tens of seconds, so the
+    number of timed steps is bounded by a time budget: min(steps, max(3, budget / step time)); `warmup` >= 1 steps
+    are capped the same way.  Returns (cpu_baseline dict, seconds per step, steps actually timed, warm-ups done)."""
+    import torch
+    root = ref_root()
+    cores = os.cpu_count() or 1
+    # thread count: calibrated on a 4-user step of the same model (cheap), as PyTorch's CPU kernels do not always
+    # scale to every core of a big host
+    cal = reference_step_fn(cfg, 4, seed, root)
+    best = None
+    for nt in sorted({min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        torch.set_num_threads(nt)
+        cal()
+        t0 = time.time()
+        cal()
+        dt = time.time() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    del cal
+    threads = best[1]
+    torch.set_num_threads(threads)
+    B = users or cfg["B"]
+    step = reference_step_fn(cfg, B, seed, root)
+    t0 = time.time()
+    step()
+    t_first = time.time() - t0
+    n_warm = 1
+    while n_warm < warmup and (n_warm + 1) * t_first < 0.25 * budget_s:
+        step()
+        n_warm += 1
+    n_timed = int(min(max(steps, 1), max(3 if steps >= 3 else steps, (budget_s - n_warm * t_first) // max(t_first, 1e-3))))
+    times = []
+    for _ in range(n_timed):
+        t0 = time.time()
+        step()
+        times.append(time.time() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
+    return dict(value=B / dt, unit="sequences/s", cores=threads, kind="reference",
+                sample=f"UNMODIFIED reference Model ({os.path.relpath(root, ROOT) if root.startswith(ROOT) else root}/"
+                       f"inbatch_sasrec_e2e_text/model), CPU fp32, {'full batch' if B == cfg['B'] else 'SAMPLE of the batch:'} B={B} (same L/T/D/BERT-base config, same "
+                       f"synthetic generator, AdamW 2 groups), {n_warm} warm-up + {n_timed} timed step(s) (median "
+                       f"{dt:.2f} s/step; min {times[0]:.2f}, max {times[-1]:.2f}); {threads} threads (calibrated on a "
+                       f"4-user step) of {cores} host cores"), dt, n_timed, n_warm
 
 
 def _synth_images(ids, seed, dev=None):
@@ -298,6 +403,11 @@ def main():
                     help="text = SASRec+BERT-base (headline, configs[2]); vision = SASRec+Swin-T (configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-users", type=int, default=4)
+    ap.add_argument("--cpu-port", action="store_true", help="reference arm / cpu_baseline: time the oracle port even "
+                    "when a copy of the unmodified reference is available")
+    ap.add_argument("--ref-users", type=int, default=0, help="reference arm: users per step (0 = the full batch B)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="wall-clock budget of the reference arm's steps (a BERT-base CPU step takes tens of seconds)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,11 +423,18 @@ def main():
         if rank != 0:
             return
         W = max(args.warmup, 1)
-        base, dt = time_cpu_oracle(cfg, args.cpu_sample_users, args.steps, W)
+        if ref_root() is not None and not args.cpu_port:
+            # the UNMODIFIED reference Model at the full batch; timed steps bounded by a wall-clock budget
+            base, dt, n_timed, n_warm = time_reference(cfg, args.steps, W, args.ref_budget_s, users=args.ref_users)
+        else:
+            # no copy of the reference on this box: the oracle port (pinned to the reference's goldens) on a sample
+            base, dt, n_timed = time_cpu_oracle(cfg, args.cpu_sample_users, args.steps, W)
+            n_warm = W
         line = {"impl": "reference", "metric": "training sequences/sec", "value": base["value"], "unit": "sequences/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": dt * 1e3,
+                "n_gpus": args.gpus, "steps": n_timed, "warmup": n_warm, "steps_requested": args.steps,
+                "warmup_requested": args.warmup, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "sample": base["sample"]},
+                "config": {"workload": workload},
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -433,7 +550,10 @@ def main():
                          "bf16": "kind::f16"}[args.mode]}
     cpu_base = None
     if not args.no_cpu_baseline and not vision:
-        cpu_base, _ = time_cpu_oracle(cfg, args.cpu_sample_users, 1, 1)
+        if ref_root() is not None and not args.cpu_port:
+            cpu_base = time_reference(cfg, 1, 1, 40.0)[0]          # 1 warm-up + 1 timed full-batch step
+        else:
+            cpu_base = time_cpu_oracle(cfg, args.cpu_sample_users, 1, 1)[0]
     line = {"metric": "training sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32 (3xTF32 tensor-core emulation)", "tf32": "tf32", "bf16": "bf16"}[args.mode],
