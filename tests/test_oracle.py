@@ -165,3 +165,33 @@ def test_mask_closed_form_equals_loops_random():
         assert not a[torch.arange(a.shape[0]), tgt][v].any()             # a valid row never masks its own target
 
     check()
+
+
+@pytest.mark.parametrize("name", ["bert_base_b4", "bert_tiny_t128_b16", "swin_t_b2", "swin_b_b2"])
+def test_oracle_matches_reference_real_configs(name):
+    """REAL encoder configurations (BERT-base 12 layers; BERT-tiny T=128 at B=16; Swin-T / Swin-B at 224x224): the
+    seeded construction reproduces the reference's weights exactly, and the oracle reproduces the unmodified
+    reference's loss, item embeddings and every parameter gradient (tests/golden/make_golden_real.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import real_cases as RC
+    c = RC.CASES[name]
+    g = RC.load_golden(name)
+    d = RC.build_inputs(c)
+    for k, v in g["input_checksums"].items():
+        assert float(d[k].double().abs().sum()) == v, k
+    if c["kind"] == "text":
+        from idvs.morec_b200.model import Model
+    else:
+        from idvs.morec_b200.model_vision import Model
+    model = RC.build_model(c, Model, d["pop_prob"])
+    cs = RC.checksums(model.state_dict())
+    for k, v in g["weight_checksums"].items():
+        assert k in cs and cs[k] == v, f"seeded construction diverged from the reference at {k}"
+    out, grads = RC.run_oracle(c, model, d)
+    nonpad = d["ids"].reshape(-1) != 0
+    if c["kind"] == "vision":
+        nonpad = torch.ones_like(nonpad)            # the reference encodes the zero image of a pad slot too
+    bad = RC.compare_to_golden(g, out.loss, out.score_embs.detach(), grads, nonpad, loss_tol=2e-5, emb_tol=5e-5, grad_tol=5e-4)
+    assert not bad, bad[:10]
