@@ -375,17 +375,26 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     rec_params = [p for n, p in model.named_parameters() if p.requires_grad and "bert_model" not in n]
     opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
                       {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
+    model.attach_optimizer(opt)      # 16-bit weight copies are written by the AdamW kernel (no per-step cast pass)
     host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
     resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    # fp16 storage needs dynamic loss scaling exactly like the reference's autocast loop (run.py:210, 245-247)
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 14)
 
     def step(ids, items, lm):
         opt.zero_grad(set_to_none=True)
         loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank)
-        loss.backward()
-        opt.step()
+        if model.compute_dtype == "fp16":
+            scaler.scale(loss).backward()
+            scaler.step(opt)         # unscale + overflow skip fused into the AdamW kernel (no host wait)
+            scaler.update()
+        else:
+            loss.backward()
+            opt.step()
         return loss
 
+    step.model = model
     return step, host, resident, h2d_bytes
 
 
@@ -396,7 +405,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="morec", choices=["morec", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "bf16"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "bf16"), choices=["fp32", "tf32", "bf16", "fp16"])
+    ap.add_argument("--no-modes", action="store_true", help="skip the short per-mode throughput block")
     ap.add_argument("--parallel", default="global", choices=["global", "local"],
                     help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")
     ap.add_argument("--workload", default="text", choices=["text", "vision"],
@@ -528,6 +538,32 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_value = cfg["B"] * world / (float(tms) / K / 1e3)
 
+    # ---------------- per-mode throughput (few steps each): makes the cost of the parity mode driver-visible
+    modes = None
+    if not vision and not args.no_modes and hasattr(step, "model"):
+        modes = {}
+        for m in ("fp32", "tf32", "bf16", "fp16"):
+            if m == args.mode:
+                modes[m] = {"seq_per_s": value, "ms_per_step": ms_step, "steps": K}
+                continue
+            step.model.set_compute_dtype(m)
+            for i in range(2):
+                step(*resident[i])
+            sync()
+            e0.record()
+            for i in range(3):
+                step(*resident[W + (i % max(K, 1))])
+            e1.record()
+            sync()
+            tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            modes[m] = {"seq_per_s": cfg["B"] * world / (float(tms) / 3 / 1e3), "ms_per_step": float(tms) / 3, "steps": 3}
+        step.model.set_compute_dtype(args.mode)
+        modes["note"] = ("fp32 = 3xTF32 parity mode (loss/logits <= 1e-3 vs the reference CPU fp32 path, tests/test_parity_gpu.py); "
+                         "fp16 = the reference's own autocast arithmetic (run.py:242) with GradScaler; measured deviations of "
+                         "every mode: profiles/r02_parity_modes.json")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -547,7 +583,7 @@ def main():
                 "note": {"fp32": "3xTF32 parity mode: 3 tensor-core passes per algorithmic FLOP and kind::tf32 runs at half "
                                  "the bf16 rate, so the attainable fraction of the bf16 peak is 1/6",
                          "tf32": "kind::tf32 runs at half the bf16 rate: attainable fraction of the bf16 peak is 1/2",
-                         "bf16": "kind::f16"}[args.mode]}
+                         "bf16": "kind::f16 on bf16 operands", "fp16": "kind::f16 on fp16 operands"}[args.mode]}
     cpu_base = None
     if not args.no_cpu_baseline and not vision:
         if ref_root() is not None and not args.cpu_port:
@@ -556,7 +592,7 @@ def main():
             cpu_base = time_cpu_oracle(cfg, args.cpu_sample_users, 1, 1)[0]
     line = {"metric": "training sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32 (3xTF32 tensor-core emulation)", "tf32": "tf32", "bf16": "bf16"}[args.mode],
+            "dtype": {"fp32": "f32 (3xTF32 tensor-core emulation)", "tf32": "tf32", "bf16": "bf16", "fp16": "fp16"}[args.mode],
             "data": "synthetic",
             "config": {"workload": workload, "mode": args.mode,
                        "parallelism": f"dp{world}" + (f" ({args.parallel}: " + ("item embeddings all-gathered, global negatives, "
@@ -567,7 +603,8 @@ def main():
                        "items_encoded": "each distinct non-pad item of the (global) batch once; pad tokens skipped"},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "host_ms_each_step": step_host_ms,
-            "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base}
+            "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline, "modes": modes,
+            "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -304,10 +304,10 @@ extern "C" int morec_attn_fwd(const void* q, const void* k, const void* v, void*
     if (!attr) {
         MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MOREC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    if (dtype != 1) attn_fwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
-    else attn_fwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    MOREC_DISPATCH_T(dtype, (attn_fwd_kernel<T><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -334,10 +334,10 @@ extern "C" int morec_attn_bwd(const void* q, const void* k, const void* v, const
     if (!attr) {
         MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MOREC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    if (dtype != 1) attn_bwd_kernel<float><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
-    else attn_bwd_kernel<__nv_bfloat16><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
+    MOREC_DISPATCH_T(dtype, (attn_bwd_kernel<T><<<blocks, AT_WARPS * 32, smem, (cudaStream_t)stream>>>(p)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

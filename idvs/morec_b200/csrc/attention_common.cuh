@@ -6,32 +6,8 @@ namespace morec {
 
 constexpr int AT_DCH = 64;      // head-dim chunk streamed through shared memory
 
-template <typename T>
-__device__ __forceinline__ float ldf(const T* p);
-template <>
-__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
-template <>
-__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-template <typename T>
-__device__ __forceinline__ void stf(T* p, float v);
-template <>
-__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
-
 // cooperative (one warp) load of rows [row0, row0+len) x cols [col0, col0+w) into tile[32][AT_DCH] (fp32), 4 elements
 // per lane per iteration (w % 4 == 0, rows 16-byte aligned)
-template <typename T>
-__device__ __forceinline__ float4 ld4(const T* p);
-template <>
-__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
-template <>
-__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-}
 template <typename T>
 __device__ __forceinline__ void load_tile(float* tile, const T* base, int ld, int row0, int len, int col0, int w,
                                           int lane) {
@@ -42,18 +18,6 @@ __device__ __forceinline__ void load_tile(float* tile, const T* base, int ld, in
     }
 }
 
-template <typename T>
-__device__ __forceinline__ void st4(T* p, float4 v);
-template <>
-__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-template <>
-__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = u;
-}
 // per-lane store of a 64-wide (or narrower) register slice to a row
 template <typename T>
 __device__ __forceinline__ void store_row(T* row, const float (&v)[AT_DCH], int w) {

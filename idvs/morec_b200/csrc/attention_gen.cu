@@ -345,6 +345,11 @@ static int dispatch_gen(const GenAttnParams& p, bool bwd, int dtype, cudaStream_
         if (nw == 2) { MOREC_GEN(__nv_bfloat16, 2); }
         MOREC_GEN(__nv_bfloat16, 4);
     }
+    if (dtype == 3) {
+        if (nw <= 1) { MOREC_GEN(__half, 1); }
+        if (nw == 2) { MOREC_GEN(__half, 2); }
+        MOREC_GEN(__half, 4);
+    }
     if (nw <= 1) { MOREC_GEN(float, 1); }
     if (nw == 2) { MOREC_GEN(float, 2); }
     MOREC_GEN(float, 4);

@@ -174,10 +174,9 @@ __device__ __forceinline__ void tc_store_stripe(T* base, int ld, int row0, int l
             if (r0 < len) *reinterpret_cast<float2*>(base + (size_t)(row0 + r0) * ld + c) = make_float2(o[m][0], o[m][1]);
             if (r1 < len) *reinterpret_cast<float2*>(base + (size_t)(row0 + r1) * ld + c) = make_float2(o[m][2], o[m][3]);
         } else {
-            if (r0 < len)
-                *reinterpret_cast<__nv_bfloat162*>(base + (size_t)(row0 + r0) * ld + c) = __floats2bfloat162_rn(o[m][0], o[m][1]);
-            if (r1 < len)
-                *reinterpret_cast<__nv_bfloat162*>(base + (size_t)(row0 + r1) * ld + c) = __floats2bfloat162_rn(o[m][2], o[m][3]);
+            constexpr bool f16 = __is_same(T, __half);
+            if (r0 < len) *reinterpret_cast<uint32_t*>(base + (size_t)(row0 + r0) * ld + c) = pack2_16(o[m][0], o[m][1], f16);
+            if (r1 < len) *reinterpret_cast<uint32_t*>(base + (size_t)(row0 + r1) * ld + c) = pack2_16(o[m][2], o[m][3], f16);
         }
     }
 }
@@ -468,7 +467,7 @@ static int tc_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
 
 // true when the tensor-core kernels cover this problem (fast modes only: C-ABI dtype 0 or 1)
 inline bool tc_attn_eligible(int dtype, int seqlen, int head_dim, int ld, int ld_o) {
-    if (!((dtype == 0 || dtype == 1) && seqlen > 0 && ld % 4 == 0 && ld_o % 4 == 0)) return false;
+    if (!((dtype == 0 || dtype == 1 || dtype == 3) && seqlen > 0 && ld % 4 == 0 && ld_o % 4 == 0)) return false;
     if (head_dim == 32 || head_dim == 64) return seqlen <= 64;
     return head_dim == 256 && seqlen <= 32;          // SASRec user tower: D = 512, 2 heads (parameters.py:28)
 }

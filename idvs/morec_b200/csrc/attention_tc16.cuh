@@ -23,15 +23,24 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// T = __nv_bfloat16 ("bf16" mode) or __half ("fp16" mode: the reference's own autocast arithmetic, run.py:242)
+template <typename T>
+__device__ __forceinline__ void mma16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (sizeof(T) == 2 && !__is_same(T, __half)) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+template <typename T>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+    return pack2_16(lo, hi, __is_same(T, __half));
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -53,8 +62,8 @@ struct Tc16Cfg {
 };
 
 // rows [row0, row0+len) x cols [col0, col0+D) -> dst[LP][SB] (bf16), rows >= len zero-filled; asynchronous
-template <int D, int LP>
-__device__ __forceinline__ void tc16_load_tile(__nv_bfloat16* dst, const __nv_bfloat16* base, int ld, int row0, int len,
+template <typename T, int D, int LP>
+__device__ __forceinline__ void tc16_load_tile(T* dst, const T* base, int ld, int row0, int len,
                                                int col0) {
     using C = Tc16Cfg<D, LP>;
     constexpr int NV = D / 8;                                    // 16-byte chunks per row
@@ -64,14 +73,14 @@ __device__ __forceinline__ void tc16_load_tile(__nv_bfloat16* dst, const __nv_bf
         const int idx = threadIdx.x + i * C::THREADS;
         const int r = idx / NV, c = (idx - r * NV) << 3;
         const bool ok = r < len;
-        const __nv_bfloat16* src = ok ? base + (size_t)(row0 + r) * ld + col0 + c : base;
+        const T* src = ok ? base + (size_t)(row0 + r) * ld + col0 + c : base;
         cp_async16(smem_u32(dst + r * C::SB + c), src, ok ? 16u : 0u);
     }
 }
 
 // acc[n] (n < NT) = X[m0 .. m0+16, :] . Y[8n .. 8n+8, :]^T over the D columns (both operands stored by rows)
-template <int D, int LP>
-__device__ __forceinline__ void tc16_rows_dot_rows(const __nv_bfloat16* X, const __nv_bfloat16* Y, int m0, int ncols,
+template <typename T, int D, int LP>
+__device__ __forceinline__ void tc16_rows_dot_rows(const T* X, const T* Y, int m0, int ncols,
                                                    float (&acc)[LP / 8][4], int lane) {
     using C = Tc16Cfg<D, LP>;
 #pragma unroll
@@ -87,16 +96,16 @@ __device__ __forceinline__ void tc16_rows_dot_rows(const __nv_bfloat16* X, const
             if (j * 16 < ncols) {
                 uint32_t b[4];
                 ldsm_x4(b, ya + (j * 16 * C::SB + kk * 16) * 2);
-                mma_bf16(acc[2 * j], a, b[0], b[1]);
-                mma_bf16(acc[2 * j + 1], a, b[2], b[3]);
+                mma16<T>(acc[2 * j], a, b[0], b[1]);
+                mma16<T>(acc[2 * j + 1], a, b[2], b[3]);
             }
         }
     }
 }
 
 // out[m] (m < MT) = sum over 16-key steps of  A (accumulator registers, rounded to bf16) . Y[16ks .., 8m ..]
-template <int D, int LP>
-__device__ __forceinline__ void tc16_regs_dot_cols(const float (&p)[LP / 8][4], const __nv_bfloat16* Y, int nrows,
+template <typename T, int D, int LP>
+__device__ __forceinline__ void tc16_regs_dot_cols(const float (&p)[LP / 8][4], const T* Y, int nrows,
                                                    float (&out)[D / 8][4], int lane) {
     using C = Tc16Cfg<D, LP>;
 #pragma unroll
@@ -106,24 +115,24 @@ __device__ __forceinline__ void tc16_regs_dot_cols(const float (&p)[LP / 8][4], 
     for (int ks = 0; ks < LP / 16; ++ks) {
         if (ks * 16 < nrows) {
             uint32_t a[4];
-            a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
-            a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
-            a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
-            a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+            a[0] = pack16<T>(p[2 * ks][0], p[2 * ks][1]);
+            a[1] = pack16<T>(p[2 * ks][2], p[2 * ks][3]);
+            a[2] = pack16<T>(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+            a[3] = pack16<T>(p[2 * ks + 1][2], p[2 * ks + 1][3]);
 #pragma unroll
             for (int mp = 0; mp < C::MT / 2; ++mp) {
                 uint32_t b[4];
                 ldsm_x4_t(b, ya + (ks * 16 * C::SB + mp * 16) * 2);
-                mma_bf16(out[2 * mp], a, b[0], b[1]);
-                mma_bf16(out[2 * mp + 1], a, b[2], b[3]);
+                mma16<T>(out[2 * mp], a, b[0], b[1]);
+                mma16<T>(out[2 * mp + 1], a, b[2], b[3]);
             }
         }
     }
 }
 
 // out[m] = sum over 16-query steps of  Sm^T[j0 .. j0+16, 16ks ..] . Y[16ks .., 8m ..]     (Sm: [LP][SSB] bf16)
-template <int D, int LP>
-__device__ __forceinline__ void tc16_smT_dot_cols(const __nv_bfloat16* Sm, const __nv_bfloat16* Y, int j0, int nrows,
+template <typename T, int D, int LP>
+__device__ __forceinline__ void tc16_smT_dot_cols(const T* Sm, const T* Y, int j0, int nrows,
                                                   float (&out)[D / 8][4], int lane) {
     using C = Tc16Cfg<D, LP>;
 #pragma unroll
@@ -139,17 +148,16 @@ __device__ __forceinline__ void tc16_smT_dot_cols(const __nv_bfloat16* Sm, const
             for (int mp = 0; mp < C::MT / 2; ++mp) {
                 uint32_t b[4];
                 ldsm_x4_t(b, ya + (ks * 16 * C::SB + mp * 16) * 2);
-                mma_bf16(out[2 * mp], a, b[0], b[1]);
-                mma_bf16(out[2 * mp + 1], a, b[2], b[3]);
+                mma16<T>(out[2 * mp], a, b[0], b[1]);
+                mma16<T>(out[2 * mp + 1], a, b[2], b[3]);
             }
         }
     }
 }
 
-template <int D, int LP>
+template <typename T, int D, int LP>
 __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(const TcAttnParams p) {
     using C = Tc16Cfg<D, LP>;
-    using T = __nv_bfloat16;
     extern __shared__ __align__(16) uint8_t tc16_smem[];
     T* Qs = reinterpret_cast<T*>(tc16_smem);
     T* Ks = Qs + C::TILE;
@@ -166,14 +174,14 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(
         tc_range(p, s, LP, row0, len);
         if (len <= 0) continue;
         __syncthreads();                                   // previous pair's readers are done with the tiles
-        tc16_load_tile<D, LP>(Qs, Q, p.ld, row0, len, colh);
-        tc16_load_tile<D, LP>(Ks, K, p.ld, row0, len, colh);
-        tc16_load_tile<D, LP>(Vs, V, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Qs, Q, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Ks, K, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Vs, V, p.ld, row0, len, colh);
         cp_async_wait_all();
         __syncthreads();
         if (m0 >= len) continue;                           // stripe of padding rows (warp-uniform)
         float acc[C::NT][4];
-        tc16_rows_dot_rows<D, LP>(Qs, Ks, m0, len, acc, lane);
+        tc16_rows_dot_rows<T, D, LP>(Qs, Ks, m0, len, acc, lane);
         tc_softmax_stripe<LP>(p, acc, s, h, m0, len, g, t);
         if (p.dropout_p > 0.f) {
             float keep[C::NT][4];
@@ -185,15 +193,14 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(
             }
         }
         float o[C::MT][4];
-        tc16_regs_dot_cols<D, LP>(acc, Vs, len, o, lane);
+        tc16_regs_dot_cols<T, D, LP>(acc, Vs, len, o, lane);
         tc_store_stripe<T, D>(O, p.ld_o, row0, len, colh, m0, o, g, t);
     }
 }
 
-template <int D, int LP>
+template <typename T, int D, int LP>
 __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(const TcAttnParams p) {
     using C = Tc16Cfg<D, LP>;
-    using T = __nv_bfloat16;
     extern __shared__ __align__(16) uint8_t tc16_smem[];
     T* Qs = reinterpret_cast<T*>(tc16_smem);
     T* Ks = Qs + C::TILE;
@@ -220,17 +227,17 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
         tc_range(p, s, LP, row0, len);
         if (len <= 0) continue;
         __syncthreads();
-        tc16_load_tile<D, LP>(Qs, Q, p.ld, row0, len, colh);
-        tc16_load_tile<D, LP>(Ks, K, p.ld, row0, len, colh);
-        tc16_load_tile<D, LP>(Vs, V, p.ld, row0, len, colh);
-        tc16_load_tile<D, LP>(Gs, dO, p.ld_o, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Qs, Q, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Ks, K, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Vs, V, p.ld, row0, len, colh);
+        tc16_load_tile<T, D, LP>(Gs, dO, p.ld_o, row0, len, colh);
         cp_async_wait_all();
         __syncthreads();
         if (m0 < len) {                                    // ---- query-stripe phase
             float pr[C::NT][4], dp[C::NT][4];
-            tc16_rows_dot_rows<D, LP>(Qs, Ks, m0, len, pr, lane);
+            tc16_rows_dot_rows<T, D, LP>(Qs, Ks, m0, len, pr, lane);
             tc_softmax_stripe<LP>(p, pr, s, h, m0, len, g, t);
-            tc16_rows_dot_rows<D, LP>(Gs, Vs, m0, len, dp, lane);        // dP~ = dO . V^T
+            tc16_rows_dot_rows<T, D, LP>(Gs, Vs, m0, len, dp, lane);        // dP~ = dO . V^T
             float keepm[C::NT][4];
             tc_keep_stripe<C::NT>(p, s * p.n_heads + h, C::NW, warp, lane, len, keepm);
             float dsum[2] = {0.f, 0.f};
@@ -246,9 +253,9 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
                 }
                 // P~ for dV (zero beyond len: pr is exactly 0 there); every 16-key block the key phase reads is written
                 *reinterpret_cast<uint32_t*>(Pm + (m0 + g) * C::SSB + n * 8 + 2 * t) =
-                    pack_bf16(pr[n][0] * keep[0], pr[n][1] * keep[1]);
+                    pack16<T>(pr[n][0] * keep[0], pr[n][1] * keep[1]);
                 *reinterpret_cast<uint32_t*>(Pm + (m0 + g + 8) * C::SSB + n * 8 + 2 * t) =
-                    pack_bf16(pr[n][2] * keep[2], pr[n][3] * keep[3]);
+                    pack16<T>(pr[n][2] * keep[2], pr[n][3] * keep[3]);
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -266,20 +273,20 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
                     }
                     dp[n][e] = ds * p.scale;
                 }
-                *reinterpret_cast<uint32_t*>(dSm + (m0 + g) * C::SSB + n * 8 + 2 * t) = pack_bf16(dp[n][0], dp[n][1]);
-                *reinterpret_cast<uint32_t*>(dSm + (m0 + g + 8) * C::SSB + n * 8 + 2 * t) = pack_bf16(dp[n][2], dp[n][3]);
+                *reinterpret_cast<uint32_t*>(dSm + (m0 + g) * C::SSB + n * 8 + 2 * t) = pack16<T>(dp[n][0], dp[n][1]);
+                *reinterpret_cast<uint32_t*>(dSm + (m0 + g + 8) * C::SSB + n * 8 + 2 * t) = pack16<T>(dp[n][2], dp[n][3]);
             }
             float dq[C::MT][4];
-            tc16_regs_dot_cols<D, LP>(dp, Ks, len, dq, lane);            // dQ = dS . K
+            tc16_regs_dot_cols<T, D, LP>(dp, Ks, len, dq, lane);            // dQ = dS . K
             tc_store_stripe<T, D>(dQ, p.ld, row0, len, colh, m0, dq, g, t);
         }
         __syncthreads();
         if (m0 < len) {                                    // ---- key-stripe phase (j0 = m0)
             // query rows read: [0, 16*ceil(len/16)), all inside stripes that ran the phase above; rows >= len hold 0
             float acc[C::MT][4];
-            tc16_smT_dot_cols<D, LP>(dSm, Qs, m0, len, acc, lane);       // dK = dS^T . Q
+            tc16_smT_dot_cols<T, D, LP>(dSm, Qs, m0, len, acc, lane);       // dK = dS^T . Q
             tc_store_stripe<T, D>(dK, p.ld, row0, len, colh, m0, acc, g, t);
-            tc16_smT_dot_cols<D, LP>(Pm, Gs, m0, len, acc, lane);        // dV = P~^T . dO
+            tc16_smT_dot_cols<T, D, LP>(Pm, Gs, m0, len, acc, lane);        // dV = P~^T . dO
             tc_store_stripe<T, D>(dV, p.ld, row0, len, colh, m0, acc, g, t);
         }
     }
@@ -291,10 +298,10 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(
     }
 }
 
-template <int D, int LP>
+template <typename T, int D, int LP>
 static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
     using C = Tc16Cfg<D, LP>;
-    size_t smem = (size_t)(bwd ? 4 * C::TILE + 2 * LP * C::SSB : 3 * C::TILE) * sizeof(__nv_bfloat16);
+    size_t smem = (size_t)(bwd ? 4 * C::TILE + 2 * LP * C::SSB : 3 * C::TILE) * sizeof(T);
     if (bwd && p.dbias) smem += (size_t)p.seqlen * p.seqlen * sizeof(float);
     int gx = p.n_seq;
     if (bwd && p.dbias) {                       // few CTAs per head: each flushes its bias-gradient tile once
@@ -304,7 +311,7 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
     if (gx < 1) gx = 1;
     dim3 grid(gx, p.n_heads);
     if (!bwd) {
-        auto kern = attn_tc16_fwd_kernel<D, LP>;
+        auto kern = attn_tc16_fwd_kernel<T, D, LP>;
         static size_t set_f = 0;                         // per instantiation: raise the opt-in limit only when it grows
         if (smem > set_f) {
             MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -312,7 +319,7 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
         }
         kern<<<grid, C::THREADS, smem, stream>>>(p);
     } else {
-        auto kern = attn_tc16_bwd_kernel<D, LP>;
+        auto kern = attn_tc16_bwd_kernel<T, D, LP>;
         static size_t set_b = 0;
         if (smem > set_b) {
             MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -326,7 +333,7 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
 
 // bf16 storage, 32/64-wide heads, 16-byte aligned rows: the cp.async / ldmatrix kernels apply
 inline bool tc16_eligible(const TcAttnParams& p, int dtype, bool bwd) {
-    if (dtype != 1 || !(p.head_dim == 32 || p.head_dim == 64) || p.seqlen > 64) return false;
+    if (!MOREC_DT_IS16(dtype) || !(p.head_dim == 32 || p.head_dim == 64) || p.seqlen > 64) return false;
     if (p.ld % 8 || p.ld_o % 8) return false;
     auto al = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
     if (!al(p.q) || !al(p.k) || !al(p.v)) return false;

@@ -19,9 +19,9 @@
 extern "C" int morec_bert_layer_fwd(const MorecBertLayerFwd* a, void* stream) {
     MOREC_CHECK_ARG(a, "bert_layer_fwd: null args");
     const int M = a->n_tok, H = a->H, I = a->I;
-    const int st = a->dtype == 1 ? 1 : 0;          // storage dtype code for the non-GEMM kernels
-    const int obf = a->dtype == 1;
-    const int es = obf ? 2 : 4;
+    const int st = MOREC_DT_IS16(a->dtype) ? a->dtype : 0;   // storage dtype code for the non-GEMM kernels
+    const int obf = st;                                      // GEMM out_dtype: same storage type as the operands
+    const int es = st ? 2 : 4;
     const float scale = 1.0f / sqrtf((float)(H / a->n_heads));
     // fused QKV projection
     RUN(morec_gemm(a->x, a->wqkv, a->qkv, nullptr, a->bqkv, nullptr, M, 3 * H, H, H, H, 3 * H, 0, 0, 0, a->dtype, obf,
@@ -53,9 +53,9 @@ extern "C" int morec_bert_layer_bwd(const MorecBertLayerBwd* a, void* stream) {
     MOREC_CHECK_ARG(a, "bert_layer_bwd: null args");
     const MorecBertLayerFwd* f = &a->fwd;
     const int M = f->n_tok, H = f->H, I = f->I;
-    const int st = f->dtype == 1 ? 1 : 0;
-    const int obf = f->dtype == 1;
-    const int es = obf ? 2 : 4;
+    const int st = MOREC_DT_IS16(f->dtype) ? f->dtype : 0;
+    const int obf = st;
+    const int es = st ? 2 : 4;
     const float scale = 1.0f / sqrtf((float)(H / f->n_heads));
     const bool drop = f->p_hidden > 0.f;
     // ---- output LayerNorm: dy (+dy2) w.r.t. x2 -> dz2 (residual stream) and dfo (branch, dropout mask applied)

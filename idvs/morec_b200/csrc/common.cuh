@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -36,6 +37,88 @@ void set_last_error(const char* fmt, ...);
 #define MOREC_LAUNCH_CHECK() MOREC_CUDA(cudaGetLastError())
 
 int num_sms();
+
+// Storage dtype codes of the C ABI: 0 = fp32, 1 = bf16, 3 = fp16 (2 = fp32 storage with 3xTF32 GEMM math; it only
+// differs from 0 inside morec_gemm).  MOREC_DISPATCH_T runs the statement with `T` bound to the element type.
+#define MOREC_DT_IS16(dt) ((dt) == 1 || (dt) == 3)
+#define MOREC_DISPATCH_T(dtype, ...)                                     \
+    do {                                                                 \
+        if ((dtype) == 1) { using T = __nv_bfloat16; __VA_ARGS__; }      \
+        else if ((dtype) == 3) { using T = __half; __VA_ARGS__; }        \
+        else { using T = float; __VA_ARGS__; }                           \
+    } while (0)
+
+// 2 x fp32 <-> one packed pair of 16-bit floats; f16 selects IEEE half instead of bfloat16 (warp-uniform runtime flag:
+// the tcgen05 epilogues serve both 16-bit storage types with one instantiation)
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, bool f16) {
+    if (f16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2_16(uint32_t u, bool f16) {
+    if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ float unpack1_16(uint16_t u, bool f16) {
+    if (f16) return __half2float(*reinterpret_cast<const __half*>(&u));
+    return __uint_as_float((uint32_t)u << 16);
+}
+
+// 4 consecutive elements <-> float4 for every storage type
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void st4<__half>(__half* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+template <>
+__device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

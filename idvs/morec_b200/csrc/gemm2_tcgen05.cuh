@@ -197,7 +197,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp == 1 && leader) {
         // ================================ MMA issuer (leader CTA only) ================================
-        constexpr uint32_t fmt = KIND == 1 ? 1u : 2u;
+        const uint32_t fmt = KIND == 1 ? (p.in_f16 ? 0u : 1u) : 2u;      // f16 / bf16 : tf32
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                                ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(C::BLOCK_N >> 3) << 17) |
                                ((uint32_t)(C::PAIR_M >> 4) << 24);
@@ -248,6 +248,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         st.aux_bar = smem_u32(&aux_bars[warp - 4]); st.aux_phase = 0; st.aux_groups = 0;
         st.c_end = 0;
         st.lane = lane;
+        st.f16 = p.out_f16 != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         if (pair < total_work) {                            // epilogue side inputs of the first tile -> L2
@@ -331,6 +332,8 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     p.accumulate = g.accumulate;
     p.out_bf16 = g.out_bf16;
     p.aux_tma = aux_tma ? 1 : 0;
+    p.in_f16 = g.dtype == 3;
+    p.out_f16 = g.out_f16;
     const int pairs_max = num_sms() / 2;
     int splits = 1;
     if (g.accumulate && g.allow_split_k) {
@@ -370,7 +373,7 @@ template <class Epi>
 int gemm_dispatch_auto(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
     if (gemm2_enabled() && g.dtype != 2 && gemm_is_wide(g.N) && g.M >= 512 && g.M > 0 && g.N > 0 && g.K > 0) {
         if (g.dtype == 0) return gemm2_launch<0, Epi>(g, ep, stream);
-        if (g.dtype == 1) return gemm2_launch<1, Epi>(g, ep, stream);
+        if (g.dtype == 1 || g.dtype == 3) return gemm2_launch<1, Epi>(g, ep, stream);
     }
     return gemm_dispatch<Epi>(g, ep, stream);
 }

@@ -16,7 +16,8 @@ struct StdEpiParams {
     const float* bias;   // [N] fp32 or null
     const void* aux;     // [M, ldaux] or null (dtype = aux_bf16 ? bf16 : fp32)
     int ldaux;
-    int aux_bf16;
+    int aux_bf16;        // side input is 16-bit
+    int aux_f16;         // ... and IEEE half rather than bfloat16
 };
 
 template <int MODE>
@@ -41,22 +42,24 @@ struct StdEpi {
                     for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __ldg(ap + j) : 0.f;
                 }
             } else {
-                const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+                const uint16_t* ap = reinterpret_cast<const uint16_t*>(ep.aux) + (size_t)row * ep.ldaux + col0;
+                const bool f16 = ep.aux_f16 != 0;
                 if (col0 + 32 <= N && (ep.ldaux & 7) == 0 && (reinterpret_cast<uintptr_t>(ep.aux) & 15) == 0) {
                     // 4 x 16-byte loads per row (the scalar form issued 32 two-byte loads, each touching 32 sectors)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap) + j);
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                        const uint32_t* h = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            a[8 * j + 2 * e] = __low2float(h[e]);
-                            a[8 * j + 2 * e + 1] = __high2float(h[e]);
+                            const float2 f = unpack2_16(h[e], f16);
+                            a[8 * j + 2 * e] = f.x;
+                            a[8 * j + 2 * e + 1] = f.y;
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? __bfloat162float(ap[j]) : 0.f;
+                    for (int j = 0; j < 32; ++j) a[j] = (col0 + j < N) ? unpack1_16(__ldg(ap + j), f16) : 0.f;
                 }
             }
         } else {
@@ -81,9 +84,16 @@ struct StdEpi {
             for (int j = 0; j < 4; ++j) r[j] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
-    __device__ __forceinline__ static float aux_raw_at(const uint4 (&r)[4], int j) {   // j compile-time after unrolling
-        const uint32_t w = reinterpret_cast<const uint32_t*>(&r[j >> 3])[(j & 7) >> 1];
-        return __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+    // unpack the 32 packed 16-bit side-input values of a chunk (F16: IEEE half, else bfloat16)
+    template <bool F16>
+    __device__ __forceinline__ static void aux_unpack(const uint4 (&r)[4], float (&a)[32]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(&r[j >> 2])[j & 3];
+            const float2 f = unpack2_16(w, F16);
+            a[2 * j] = f.x;
+            a[2 * j + 1] = f.y;
+        }
     }
 
     // this warp's chunk range [c_lo, c_end) of the tile at n0 (column group cg of ncg)
@@ -189,15 +199,11 @@ struct StdEpi {
             }
             st.put(&tmC2, d, c, obf, 1, 2);
         } else if constexpr (MODE == MOREC_EPI_MUL_AUX) {
-            if (have_raw) {
+            float a[32];
+            if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
+            else load_aux(ep, a, row, col0, s.M, s.N);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] *= aux_raw_at(araw, j);
-            } else {
-                float a[32];
-                load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] *= a[j];
-            }
+            for (int j = 0; j < 32; ++j) x[j] *= a[j];
         } else if constexpr (MODE == MOREC_EPI_GELU_NOSAVE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = FAST ? gelu_fast(x[j]) : gelu_erf(x[j]);
@@ -205,28 +211,17 @@ struct StdEpi {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
         } else if constexpr (MODE == MOREC_EPI_MUL_GELU_GRAD) {
-            if (have_raw) {
+            float a[32];
+            if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
+            else load_aux(ep, a, row, col0, s.M, s.N);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float a = aux_raw_at(araw, j);
-                    x[j] *= FAST ? gelu_fast_grad(a) : gelu_erf_grad(a);
-                }
-            } else {
-                float a[32];
-                load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] *= FAST ? gelu_fast_grad(a[j]) : gelu_erf_grad(a[j]);
-            }
+            for (int j = 0; j < 32; ++j) x[j] *= FAST ? gelu_fast_grad(a[j]) : gelu_erf_grad(a[j]);
         } else if constexpr (MODE == MOREC_EPI_MUL_RELU_GRAD) {
-            if (have_raw) {
+            float a[32];
+            if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
+            else load_aux(ep, a, row, col0, s.M, s.N);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = aux_raw_at(araw, j) > 0.f ? x[j] : 0.f;
-            } else {
-                float a[32];
-                load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
         }
         st.put(&tmC, x, c, obf, 0, ns);
         st.end_chunk(c, n0, row0, obf, s.accumulate != 0, ns);

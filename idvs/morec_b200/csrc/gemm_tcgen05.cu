@@ -61,7 +61,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inne
 // ------------------------------------------------------------------------------------------------
 extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux,
                           int M, int N, int K, int lda, int ldb, int ldc, int ldaux, int a_mn_major, int b_mn_major,
-                          int dtype, int out_bf16, int epilogue, float alpha, int accumulate, void* stream) {
+                          int dtype, int out_dtype, int epilogue, float alpha, int accumulate, void* stream) {
     using namespace morec;
     MOREC_CHECK_ARG(A && B && C, "morec_gemm: null operand");
     MOREC_CHECK_ARG(epilogue >= MOREC_EPI_LINEAR && epilogue <= MOREC_EPI_MUL_AUX, "morec_gemm: bad epilogue %d",
@@ -76,12 +76,14 @@ extern "C" int morec_gemm(const void* A, const void* B, void* C, void* C2, const
     g.M = M; g.N = N; g.K = K;
     g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     g.a_mn = a_mn_major; g.b_mn = b_mn_major;
-    g.dtype = dtype; g.out_bf16 = out_bf16;
+    MOREC_CHECK_ARG(out_dtype == 0 || out_dtype == 1 || out_dtype == 3, "morec_gemm: out_dtype must be 0 (fp32), 1 (bf16) or 3 (fp16)");
+    g.dtype = dtype; g.out_bf16 = out_dtype != 0; g.out_f16 = out_dtype == 3;
     g.accumulate = accumulate; g.allow_split_k = accumulate;
     g.aux = aux; g.ldaux = ldaux;
     StdEpiParams ep;
     ep.mode = epilogue; ep.alpha = alpha; ep.bias = bias; ep.aux = aux; ep.ldaux = ldaux;
-    ep.aux_bf16 = (dtype == 1);
+    ep.aux_bf16 = MOREC_DT_IS16(dtype);
+    ep.aux_f16 = dtype == 3;
     cudaStream_t st = (cudaStream_t)stream;
     switch (epilogue) {
         case MOREC_EPI_LINEAR: return gemm_std_run_0(g, ep, st);

@@ -32,8 +32,9 @@ struct GemmArgs {
     int M, N, K;
     int lda, ldb, ldc;     // leading dimensions in elements
     int a_mn, b_mn;        // 0: operand is [rows, K] row-major (K-major); 1: [K, rows] row-major (MN-major)
-    int dtype;             // 0: fp32 storage / kind::tf32, 1: bf16 storage / kind::f16
-    int out_bf16;          // output element type of C/C2 (0: fp32, 1: bf16)
+    int dtype;             // 0: fp32 storage / kind::tf32, 1: bf16 storage / kind::f16, 2: fp32 / 3xTF32, 3: fp16 / kind::f16
+    int out_bf16;          // output element type of C/C2: 0 fp32, non-zero 16-bit (bf16, or fp16 when out_f16)
+    int out_f16 = 0;       // 16-bit outputs are IEEE half instead of bfloat16
     int accumulate;        // 1: C += result via TMA reduce-add (C must be fp32); enables split-K
     int allow_split_k;
     const void* aux = nullptr;   // epilogue side input [M, ldaux] (activation-gradient epilogues), element type of the operands
@@ -54,7 +55,9 @@ struct TileSched {
     int a_mn, b_mn;
     int accumulate;
     int out_bf16;
-    int aux_tma;           // 1: tmC2 describes the epilogue side input (bf16) and the CTA-pair kernel stages it by TMA
+    int aux_tma;           // 1: tmC2 describes the epilogue side input (16-bit) and the CTA-pair kernel stages it by TMA
+    int in_f16;            // KIND 1 operands are IEEE half (instruction-descriptor format 0) instead of bfloat16 (1)
+    int out_f16;           // 16-bit outputs are IEEE half
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -113,6 +116,7 @@ struct EpiStore {
     uint32_t aux_bar;         // mbarrier of this warp's side-input TMA loads (0: not used by this kernel)
     uint32_t aux_phase;
     int aux_groups;           // side-input groups staged for the current tile (0: read the side input directly)
+    bool f16;                 // 16-bit outputs are IEEE half (else bfloat16)
     const CUtensorMap* tm[2]; // output tensor map per stream (0: C, 1: C2)
 
     // The staging memory is used as TWO halves when it has at least two sub-buffers per output stream: a group is
@@ -148,13 +152,9 @@ struct EpiStore {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int pj = (half * 4 + j) ^ (lane & 7);
-                __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * j], x[8 * j + 1]);
-                __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * j + 2], x[8 * j + 3]);
-                __nv_bfloat162 cc = __floats2bfloat162_rn(x[8 * j + 4], x[8 * j + 5]);
-                __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * j + 6], x[8 * j + 7]);
                 uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-                u.z = *reinterpret_cast<uint32_t*>(&cc); u.w = *reinterpret_cast<uint32_t*>(&d);
+                u.x = pack2_16(x[8 * j], x[8 * j + 1], f16); u.y = pack2_16(x[8 * j + 2], x[8 * j + 3], f16);
+                u.z = pack2_16(x[8 * j + 4], x[8 * j + 5], f16); u.w = pack2_16(x[8 * j + 6], x[8 * j + 7], f16);
                 *reinterpret_cast<uint4*>(rowp + pj * 16) = u;
             }
         }
@@ -299,7 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ================================ MMA issuer ================================
         // instruction descriptor: D=f32 [4,6), A fmt [7,10), B fmt [10,13), A major [15], B major [16],
         // N>>3 [17,23), M>>4 [24,29)
-        constexpr uint32_t fmt = KIND == 1 ? 1u : 2u;   // bf16 : tf32
+        const uint32_t fmt = KIND == 1 ? (p.in_f16 ? 0u : 1u) : 2u;   // f16 / bf16 : tf32
         constexpr int MK = KIND == 1 ? 1 : 0;           // tc_mma kind
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                                ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
@@ -388,6 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         st.aux_bar = 0; st.aux_phase = 0; st.aux_groups = 0;
         st.c_end = 0;
         st.lane = lane;
+        st.f16 = p.out_f16 != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         if ((int)blockIdx.x < total_work) {                 // epilogue side inputs of the first tile -> L2
@@ -469,6 +470,8 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
     p.accumulate = g.accumulate;
     p.out_bf16 = g.out_bf16;
     p.aux_tma = 0;
+    p.in_f16 = g.dtype == 3;
+    p.out_f16 = g.out_f16;
     const int sms = num_sms();
     int splits = 1;
     if (g.accumulate && g.allow_split_k) {
@@ -500,11 +503,11 @@ inline int gemm_block_n(int N, int dtype) { return dtype == 2 ? 128 : (gemm_is_w
 template <class Epi>
 int gemm_dispatch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
     MOREC_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-    MOREC_CHECK_ARG(g.dtype >= 0 && g.dtype <= 2, "gemm: dtype must be 0 (fp32/tf32), 1 (bf16) or 2 (fp32/3xtf32)");
+    MOREC_CHECK_ARG(g.dtype >= 0 && g.dtype <= 3, "gemm: dtype must be 0 (fp32/tf32), 1 (bf16), 2 (fp32/3xtf32) or 3 (fp16)");
     const bool wide = gemm_is_wide(g.N);
     if (g.dtype == 2) return gemm_launch<2, 128, Epi>(g, ep, stream);   // doubled stages: 128-wide tiles only
     if (g.dtype == 0) return wide ? gemm_launch<0, 256, Epi>(g, ep, stream) : gemm_launch<0, 128, Epi>(g, ep, stream);
-    return wide ? gemm_launch<1, 256, Epi>(g, ep, stream) : gemm_launch<1, 128, Epi>(g, ep, stream);
+    return wide ? gemm_launch<1, 256, Epi>(g, ep, stream) : gemm_launch<1, 128, Epi>(g, ep, stream);   // bf16 and fp16
 }
 
 }  // namespace morec

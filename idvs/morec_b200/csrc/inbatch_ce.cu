@@ -264,7 +264,7 @@ extern "C" int morec_inbatch_ce_dlogits(const void* P, const void* E, const uint
     GemmArgs g{};
     g.A = P; g.B = E; g.C = dS; g.C2 = nullptr;
     g.M = B * L; g.N = C; g.K = D; g.lda = D; g.ldb = D; g.ldc = ldds;
-    g.dtype = dtype; g.out_bf16 = dtype == 1;
+    g.dtype = dtype; g.out_bf16 = MOREC_DT_IS16(dtype); g.out_f16 = dtype == 3;
     CeParams ep{};
     ep.member = member; ep.pad = pad; ep.log_pop = log_pop; ep.L = L; ep.Wc = (C + 31) / 32; ep.col_offset = col_offset;
     ep.row_lse = row_lse; ep.log_mask = log_mask; ep.grad_out = grad_out; ep.n_valid = n_valid;

@@ -16,30 +16,6 @@ namespace morec {
 constexpr int LN_WARPS = 8;
 constexpr int LN_MAXV = 16;   // float4 per lane -> H <= 2048 (kernels are templated on the per-lane vector count NV)
 
-template <typename T>
-__device__ __forceinline__ float4 load4(const T* p);
-template <>
-__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
-template <>
-__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-}
-template <typename T>
-__device__ __forceinline__ void store4(T* p, float4 v);
-template <>
-__device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-template <>
-__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = u;
-}
-
 // Dropout of one float4 (4 consecutive columns) of row `row`: rows are paired, the Philox block of (row >> 1, float4
 // column i) carries the decisions of both rows -- row & 1 selects the 16-bit half of each word.
 __device__ __forceinline__ float4 drop4_bits(float4 v, uint4 r, int half, uint32_t th16, float scale) {
@@ -80,9 +56,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnFwdParams
         for (int j = 0; j < NV; ++j) {
             const int i = lane + 32 * j;
             if (i < nv) {
-                float4 v = load4<T>(xr + 4 * i);
+                float4 v = ld4<T>(xr + 4 * i);
                 if (p.p_pre > 0.f) v = drop4_bits(v, drop_block(p.seed, p.off_pre, row, nv, i), row & 1, th_pre, sc_pre);
-                if (rr) { const float4 r = load4<T>(rr + 4 * i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+                if (rr) { const float4 r = ld4<T>(rr + 4 * i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
                 if (pr) { const float4 r = *reinterpret_cast<const float4*>(pr + 4 * i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
                 z[j] = v;
                 s += v.x + v.y + v.z + v.w;
@@ -113,9 +89,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnFwdParams
                 o.y = (z[j].y - mean) * rstd * g.y + b.y;
                 o.z = (z[j].z - mean) * rstd * g.z + b.z;
                 o.w = (z[j].w - mean) * rstd * g.w + b.w;
-                if (ypr) store4<T>(ypr + 4 * i, o);
+                if (ypr) st4<T>(ypr + 4 * i, o);
                 if (p.p_post > 0.f) o = drop4_bits(o, drop_block(p.seed, p.off_post, row, nv, i), row & 1, th_post, sc_post);
-                store4<T>(yr + 4 * i, o);
+                st4<T>(yr + 4 * i, o);
             }
         }
     }
@@ -171,9 +147,9 @@ __global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 3) ln_bwd_kernel(co
             rs[r] = 0.f;
             if (act && row < p.M) {
                 const size_t o = (size_t)row * p.H + 4 * c;
-                d[r] = load4<T>(dyb + o);
-                if (dy2b) { const float4 e = load4<T>(dy2b + o); d[r].x += e.x; d[r].y += e.y; d[r].z += e.z; d[r].w += e.w; }
-                yv[r] = load4<T>(yb + o);
+                d[r] = ld4<T>(dyb + o);
+                if (dy2b) { const float4 e = ld4<T>(dy2b + o); d[r].x += e.x; d[r].y += e.y; d[r].z += e.z; d[r].w += e.w; }
+                yv[r] = ld4<T>(yb + o);
                 rs[r] = p.rstd[row];
             }
         }
@@ -229,11 +205,11 @@ __global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 3) ln_bwd_kernel(co
                 z.y = rstd * (d[r].y - m1 - yv[r].y * m2);
                 z.z = rstd * (d[r].z - m1 - yv[r].z * m2);
                 z.w = rstd * (d[r].w - m1 - yv[r].w * m2);
-                store4<T>(dzb + o, z);
+                st4<T>(dzb + o, z);
                 if (p.dpos) atomicAdd(reinterpret_cast<float4*>(p.dpos + (size_t)(row % p.pos_period) * p.H + 4 * c), z);
                 float4 b = z;
                 if (p.p_pre > 0.f) b = drop4_bits(z, rb[r >> 1], r & 1, th_pre, sc_pre);
-                if (dxb) store4<T>(dxb + o, b);
+                if (dxb) st4<T>(dxb + o, b);
                 ax.x += b.x; ax.y += b.y; ax.z += b.z; ax.w += b.w;
             }
         }
@@ -266,8 +242,7 @@ extern "C" int morec_layernorm_fwd(const void* x, const void* residual, const fl
     const int nvl = (H / 4 + 31) / 32;
 #define LN_FWD(NVV)                                                                                         \
     do {                                                                                                    \
-        if (dtype == 0) ln_fwd_kernel<float, NVV><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(p);    \
-        else ln_fwd_kernel<__nv_bfloat16, NVV><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(p);       \
+        MOREC_DISPATCH_T(dtype, (ln_fwd_kernel<T, NVV><<<blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(p)));     \
     } while (0)
     if (nvl <= 2) LN_FWD(2); else if (nvl <= 4) LN_FWD(4); else if (nvl <= 6) LN_FWD(6); else if (nvl <= 8) LN_FWD(8); else LN_FWD(16);
 #undef LN_FWD
@@ -289,13 +264,13 @@ extern "C" int morec_layernorm_bwd(const void* dy, const void* dy2, const void* 
     const int threads = ((H / 4 + 31) / 32) * 32;                 // <= 512
     // persistent grid = resident CTAs (occupancy query): 4 CTAs/SM were launched where 3 fit, and the second partial
     // wave cost a third of the kernel (ncu: 1.33 waves)
-    static int occ_f32[17] = {0}, occ_bf16[17] = {0};
-    int& occ = (dtype == 1 ? occ_bf16 : occ_f32)[threads / 32];
+    static int occ_f32[17] = {0}, occ_16[17] = {0};          // (bf16 and fp16 instantiations have the same footprint)
+    int& occ = (MOREC_DT_IS16(dtype) ? occ_16 : occ_f32)[threads / 32];
     const bool big = threads > 256;
     if (occ == 0) {
         cudaError_t e;
-        if (dtype == 1) e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<__nv_bfloat16, true>, threads, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<__nv_bfloat16, false>, threads, 0);
+        if (MOREC_DT_IS16(dtype)) e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<__nv_bfloat16, true>, threads, 0)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<__nv_bfloat16, false>, threads, 0);
         else e = big ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<float, true>, threads, 0)
                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_bwd_kernel<float, false>, threads, 0);
         MOREC_CUDA(e);
@@ -305,13 +280,8 @@ extern "C" int morec_layernorm_bwd(const void* dy, const void* dy2, const void* 
     const int cap = num_sms() * occ;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == 1) {
-        if (big) ln_bwd_kernel<__nv_bfloat16, true><<<blocks, threads, 0, st>>>(p);
-        else ln_bwd_kernel<__nv_bfloat16, false><<<blocks, threads, 0, st>>>(p);
-    } else {
-        if (big) ln_bwd_kernel<float, true><<<blocks, threads, 0, st>>>(p);
-        else ln_bwd_kernel<float, false><<<blocks, threads, 0, st>>>(p);
-    }
+    if (big) MOREC_DISPATCH_T(dtype, (ln_bwd_kernel<T, true><<<blocks, threads, 0, st>>>(p)));
+    else MOREC_DISPATCH_T(dtype, (ln_bwd_kernel<T, false><<<blocks, threads, 0, st>>>(p)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

@@ -11,30 +11,6 @@
 
 namespace morec {
 
-template <typename T>
-__device__ __forceinline__ float4 ld4(const T* p);
-template <>
-__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
-template <>
-__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
-}
-template <typename T>
-__device__ __forceinline__ void st4(T* p, float4 v);
-template <>
-__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-template <>
-__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&a);
-    u.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = u;
-}
-
 // ---------------------------------------------------------------------------------------------- BERT embeddings
 template <typename T>
 __global__ void bert_embed_fwd_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ pos,
@@ -220,17 +196,19 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ a
 }
 
 // ---------------------------------------------------------------------------------------------- casts
-__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+template <typename T>
+__global__ void cast_f32_to_16_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-        st4<__nv_bfloat16>(dst + 4 * i, *reinterpret_cast<const float4*>(src + 4 * i));
+        st4<T>(dst + 4 * i, *reinterpret_cast<const float4*>(src + 4 * i));
 }
 
 // many tensors in ONE launch (bf16 weight shadows of a whole tower: 49 casts for BERT-base): same chunk table as AdamW
 struct CastTensor {
-    const float* src; __nv_bfloat16* dst; long long n;
+    const float* src; void* dst; long long n;
 };
 constexpr int CAST_CHUNK = 16384;
 __device__ __forceinline__ int find_tensor(const int* __restrict__ chunk_start, int n_tensors, int chunk);
+template <typename T>
 __global__ void __launch_bounds__(256) cast_multi_kernel(const CastTensor* __restrict__ tensors,
                                                          const int* __restrict__ chunk_start, int n_tensors, int n_chunks) {
     for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
@@ -239,10 +217,11 @@ __global__ void __launch_bounds__(256) cast_multi_kernel(const CastTensor* __res
         const long long e0 = (long long)(ci - chunk_start[t]) * CAST_CHUNK;
         const long long e1 = min(ch.n, e0 + CAST_CHUNK);
         for (long long i = e0 + threadIdx.x * 4; i < e1; i += blockDim.x * 4) {
+            T* dst = reinterpret_cast<T*>(ch.dst);
             if (i + 4 <= e1) {
-                st4<__nv_bfloat16>(ch.dst + i, *reinterpret_cast<const float4*>(ch.src + i));
+                st4<T>(dst + i, *reinterpret_cast<const float4*>(ch.src + i));
             } else {
-                for (long long k = i; k < e1; ++k) ch.dst[k] = __float2bfloat16(ch.src[k]);
+                for (long long k = i; k < e1; ++k) stf<T>(dst + k, ch.src[k]);
             }
         }
     }
@@ -252,8 +231,8 @@ __global__ void __launch_bounds__(256) cast_multi_kernel(const CastTensor* __res
 // One entry per parameter tensor; CTAs walk fixed-size chunks and find their tensor by binary search in the
 // exclusive prefix sum of per-tensor chunk counts (chunk_start[n_tensors + 1]).
 struct AdamTensor {
-    float* p; const float* g; float* m; float* v; __nv_bfloat16* p_bf16;
-    int n; float lr, wd;
+    float* p; const float* g; float* m; float* v; void* p16;   // p16: optional 16-bit copy of the updated parameter
+    int n; float lr, wd, beta1, beta2, eps;
 };
 constexpr int ADAM_CHUNK = 16384;
 
@@ -266,20 +245,24 @@ __device__ __forceinline__ int find_tensor(const int* __restrict__ chunk_start, 
     return lo;
 }
 
+template <typename T16>
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ tensors,
                                                           const int* __restrict__ chunk_start, int n_tensors,
-                                                          int n_chunks, float beta1, float beta2, float eps, float bc1,
-                                                          float bc2, const float* __restrict__ inv_scale,
+                                                          int n_chunks, const float* __restrict__ step_dev,
+                                                          const float* __restrict__ grad_scale,
                                                           const float* __restrict__ found_inf) {
     // found_inf != 0 -> skip the whole step (GradScaler semantics)
     if (found_inf && *found_inf != 0.f) return;
-    const float gs = inv_scale ? *inv_scale : 1.f;
-    const float rs2 = rsqrtf(bc2);
+    const float gs = grad_scale ? 1.f / *grad_scale : 1.f;
+    const float step_no = *step_dev;             // already advanced by adam_step_kernel
     for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
         const int t = find_tensor(chunk_start, n_tensors, ci);
         const AdamTensor ch = tensors[t];
         const int e0 = (ci - chunk_start[t]) * ADAM_CHUNK;
         const int e1 = min(ch.n, e0 + ADAM_CHUNK);
+        const float beta1 = ch.beta1, beta2 = ch.beta2, eps = ch.eps;
+        const float bc1 = 1.f - powf(beta1, step_no), bc2 = 1.f - powf(beta2, step_no);
+        const float rs2 = rsqrtf(bc2);
         const float decay = 1.f - ch.lr * ch.wd, step = ch.lr / bc1;
         for (int i = e0 + threadIdx.x * 4; i < e1; i += blockDim.x * 4) {
             if (i + 4 <= e1) {
@@ -299,7 +282,7 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
                 *reinterpret_cast<float4*>(ch.p + i) = p;
                 *reinterpret_cast<float4*>(ch.m + i) = m;
                 *reinterpret_cast<float4*>(ch.v + i) = v;
-                if (ch.p_bf16) st4<__nv_bfloat16>(ch.p_bf16 + i, p);
+                if (ch.p16) st4<T16>(reinterpret_cast<T16*>(ch.p16) + i, p);
             } else {
                 for (int k = i; k < e1; ++k) {
                     const float gg = ch.g[k] * gs;
@@ -308,11 +291,16 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
                     const float vk = beta2 * ch.v[k] + (1.f - beta2) * gg * gg;
                     pk -= step * (mk / (sqrtf(vk) * rs2 + eps));
                     ch.p[k] = pk; ch.m[k] = mk; ch.v[k] = vk;
-                    if (ch.p_bf16) ch.p_bf16[k] = __float2bfloat16(pk);
+                    if (ch.p16) stf<T16>(reinterpret_cast<T16*>(ch.p16) + k, pk);
                 }
             }
         }
     }
+}
+
+// step += 1 unless an overflow was found (runs after grad_check_kernel, before adamw_multi_kernel)
+__global__ void adam_step_kernel(float* __restrict__ step, const float* __restrict__ found_inf) {
+    if (!(found_inf && *found_inf != 0.f)) *step += 1.f;
 }
 
 // found_inf = 1 if any gradient is inf/nan
@@ -362,8 +350,7 @@ extern "C" int morec_bert_embed_fwd(const int64_t* ids, const int32_t* pos, cons
     MOREC_CHECK_ARG(H % 4 == 0, "bert_embed_fwd: H %% 4 != 0");
     if (n_tok <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n_tok * (H / 4), 256);
-    if (dtype == 0) bert_embed_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(ids, pos, word, posemb, type0, (float*)out, n_tok, H);
-    else bert_embed_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(ids, pos, word, posemb, type0, (__nv_bfloat16*)out, n_tok, H);
+    MOREC_DISPATCH_T(dtype, (bert_embed_fwd_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(ids, pos, word, posemb, type0, (T*)out, n_tok, H)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -373,8 +360,7 @@ extern "C" int morec_bert_embed_bwd(const void* dz, const int64_t* ids, const in
     MOREC_CHECK_ARG(dz && ids && pos, "bert_embed_bwd: null pointer");
     if (n_tok <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n_tok * (H / 4), 256);
-    if (dtype == 0) bert_embed_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dz, ids, pos, dword, dposemb, n_tok, H);
-    else bert_embed_bwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dz, ids, pos, dword, dposemb, n_tok, H);
+    MOREC_DISPATCH_T(dtype, (bert_embed_bwd_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)dz, ids, pos, dword, dposemb, n_tok, H)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -386,10 +372,15 @@ extern "C" int morec_gather_rows(const void* src, const int32_t* idx, void* dst,
     if (n <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n * (H / 4), 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == 0 && dst_dtype == 0) gather_rows_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, idx, (float*)dst, n, H, ld_src, ld_dst);
-    else if (src_dtype == 0 && dst_dtype == 1) gather_rows_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
-    else if (src_dtype == 1 && dst_dtype == 1) gather_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, n, H, ld_src, ld_dst);
-    else gather_rows_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (float*)dst, n, H, ld_src, ld_dst);
+    MOREC_CHECK_ARG(!(MOREC_DT_IS16(src_dtype) && MOREC_DT_IS16(dst_dtype) && src_dtype != dst_dtype),
+                    "gather_rows: bf16 <-> fp16 conversion is not supported");
+    if (src_dtype == 0 || src_dtype == 2) {
+        MOREC_DISPATCH_T(dst_dtype, (gather_rows_kernel<float, T><<<g, 256, 0, st>>>((const float*)src, idx, (T*)dst, n, H, ld_src, ld_dst)));
+    } else if (dst_dtype == 0 || dst_dtype == 2) {
+        MOREC_DISPATCH_T(src_dtype, (gather_rows_kernel<T, float><<<g, 256, 0, st>>>((const T*)src, idx, (float*)dst, n, H, ld_src, ld_dst)));
+    } else {
+        MOREC_DISPATCH_T(src_dtype, (gather_rows_kernel<T, T><<<g, 256, 0, st>>>((const T*)src, idx, (T*)dst, n, H, ld_src, ld_dst)));
+    }
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -419,8 +410,7 @@ extern "C" int morec_scatter_add_rows(const void* src, const int32_t* idx, float
     MOREC_CHECK_ARG(H % 4 == 0 && ld_src % 4 == 0, "scatter_add_rows: H/ld must be multiples of 4");
     if (n <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n * (H / 4), 256);
-    if (src_dtype == 0) scatter_add_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, idx, dst, n, H, ld_src, ld_dst);
-    else scatter_add_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, idx, dst, n, H, ld_src, ld_dst);
+    MOREC_DISPATCH_T(src_dtype, (scatter_add_rows_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)src, idx, dst, n, H, ld_src, ld_dst)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -433,8 +423,7 @@ extern "C" int morec_scale_add_rows(const void* x, const void* y, const int32_t*
     if (n <= 0) return MOREC_OK;
     if (rows_per_group <= 0) rows_per_group = 1;
     const int g = grid_for((size_t)n * (H / 4), 256);
-    if (dtype == 0) scale_add_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)y, idx, group_scale, rows_per_group, alpha, (float*)out, n, H, ld_y);
-    else scale_add_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, idx, group_scale, rows_per_group, alpha, (__nv_bfloat16*)out, n, H, ld_y);
+    MOREC_DISPATCH_T(dtype, (scale_add_rows_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, idx, group_scale, rows_per_group, alpha, (T*)out, n, H, ld_y)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -444,8 +433,7 @@ extern "C" int morec_mean_rows(const void* x, void* out, int n_groups, int rows_
     MOREC_CHECK_ARG(H % 4 == 0 && rows_per_group > 0, "mean_rows: bad shape");
     if (n_groups <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n_groups * (H / 4), 256);
-    if (dtype == 0) mean_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)out, n_groups, rows_per_group, H);
-    else mean_rows_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n_groups, rows_per_group, H);
+    MOREC_DISPATCH_T(dtype, (mean_rows_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, n_groups, rows_per_group, H)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -460,8 +448,7 @@ extern "C" int morec_colsum(const void* x, float* out, int M, int N, int ld, int
     if (rows_per < 64) rows_per = 64;
     gy = (M + rows_per - 1) / rows_per;
     dim3 grid(gx, gy);
-    if (dtype == 0) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, out, M, N, ld, rows_per);
-    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, M, N, ld, rows_per);
+    MOREC_DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, out, M, N, ld, rows_per)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -471,30 +458,31 @@ extern "C" int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t
     MOREC_CHECK_ARG(n % 4 == 0, "act_bwd: n %% 4 != 0");
     if (n <= 0) return MOREC_OK;
     const int g = grid_for((size_t)n / 4, 256);
-    if (dtype == 0) act_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)aux, (float*)out, (size_t)n / 4, mode);
-    else act_bwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, (__nv_bfloat16*)out, (size_t)n / 4, mode);
+    MOREC_DISPATCH_T(dtype, (act_bwd_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)aux, (T*)out, (size_t)n / 4, mode)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
 
-extern "C" int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+extern "C" int morec_cast_f32_to_16(const float* src, void* dst, int64_t n, int dst_dtype, void* stream) {
     MOREC_CHECK_ARG(src && dst, "cast: null pointer");
     MOREC_CHECK_ARG(n % 4 == 0, "cast: n %% 4 != 0");
+    MOREC_CHECK_ARG(MOREC_DT_IS16(dst_dtype), "cast: dst_dtype must be 1 (bf16) or 3 (fp16)");
     if (n <= 0) return MOREC_OK;
-    cast_f32_to_bf16_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (size_t)n / 4);
+    MOREC_DISPATCH_T(dst_dtype, (cast_f32_to_16_kernel<T><<<grid_for((size_t)n / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, (size_t)n / 4)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
 
 extern "C" int morec_cast_chunk_elems(void) { return CAST_CHUNK; }
 
-extern "C" int morec_cast_f32_to_bf16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
-                                            void* stream) {
+extern "C" int morec_cast_f32_to_16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
+                                          int dst_dtype, void* stream) {
     MOREC_CHECK_ARG(tensors && chunk_start, "cast_multi: null table");
     static_assert(sizeof(CastTensor) == sizeof(MorecCastTensor), "ABI struct mismatch");
     if (n_chunks <= 0 || n_tensors <= 0) return MOREC_OK;
     const int grid = n_chunks < num_sms() * 8 ? n_chunks : num_sms() * 8;
-    cast_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const CastTensor*)tensors, chunk_start, n_tensors, n_chunks);
+    MOREC_CHECK_ARG(MOREC_DT_IS16(dst_dtype), "cast_multi: dst_dtype must be 1 (bf16) or 3 (fp16)");
+    MOREC_DISPATCH_T(dst_dtype, (cast_multi_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const CastTensor*)tensors, chunk_start, n_tensors, n_chunks)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }
@@ -503,20 +491,25 @@ extern "C" int morec_cast_f32_to_bf16_multi(const void* tensors, const int32_t* 
 extern "C" int morec_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
 extern "C" int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
-                                 float beta1, float beta2, float eps, int step, const float* inv_scale,
-                                 float* found_inf, int check_finite, void* stream) {
-    MOREC_CHECK_ARG(tensors && chunk_start, "adamw_multi: null table");
+                                 float* step, const float* grad_scale, float* found_inf, int check_finite,
+                                 int p16_dtype, void* stream) {
+    MOREC_CHECK_ARG(tensors && chunk_start && step, "adamw_multi: null table / step");
     static_assert(sizeof(AdamTensor) == sizeof(MorecAdamTensor), "ABI struct mismatch");
     if (n_chunks <= 0 || n_tensors <= 0) return MOREC_OK;
-    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     const int grid = n_chunks < num_sms() * 8 ? n_chunks : num_sms() * 8;
     if (check_finite && found_inf) {
         grad_check_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors,
                                                                  n_chunks, found_inf);
         MOREC_LAUNCH_CHECK();
     }
-    adamw_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors, n_chunks,
-                                                              beta1, beta2, eps, bc1, bc2, inv_scale, found_inf);
+    adam_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step, found_inf);
+    MOREC_LAUNCH_CHECK();
+    if (p16_dtype == 3)
+        adamw_multi_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors,
+                                                                          n_chunks, step, grad_scale, found_inf);
+    else
+        adamw_multi_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)tensors, chunk_start, n_tensors,
+                                                                                 n_chunks, step, grad_scale, found_inf);
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

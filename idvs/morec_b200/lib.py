@@ -50,9 +50,9 @@ def load():
         "morec_scatter_add_rows": [P, P, P, I, I, I, I, I, P],
         "morec_colsum": [P, P, I, I, I, I, P],
         "morec_act_bwd": [P, P, P, L, I, I, P],
-        "morec_cast_f32_to_bf16": [P, P, L, P],
-        "morec_cast_f32_to_bf16_multi": [P, P, I, I, P],
-        "morec_adamw_multi": [P, P, I, I, F, F, F, I, P, P, I, P],
+        "morec_cast_f32_to_16": [P, P, L, I, P],
+        "morec_cast_f32_to_16_multi": [P, P, I, I, I, P],
+        "morec_adamw_multi": [P, P, I, I, P, P, P, I, I, P],
         "morec_clock_probe": [P, P],
         "morec_mask_row_lens": [P, I, I, I, P, P],
         "morec_pack_tokens": [P, I, I, P, P, I, P, P, P],
@@ -187,6 +187,8 @@ def gemm_dtype_code(t: torch.Tensor) -> int:
         return 2 if _FP32_X3 else 0
     if t.dtype == torch.bfloat16:
         return 1
+    if t.dtype == torch.float16:
+        return 3
     raise MorecError(f"unsupported dtype {t.dtype}")
 
 
@@ -256,7 +258,7 @@ def d2h_many(tensors):
 
 # enum mirrors
 EPI_LINEAR, EPI_GELU, EPI_GELU_NOSAVE, EPI_RELU, EPI_MUL_GELU_GRAD, EPI_MUL_RELU_GRAD, EPI_GELU_DGELU, EPI_MUL_AUX = range(8)
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 3
 
 
 def dtype_code(t: torch.Tensor) -> int:
@@ -264,6 +266,8 @@ def dtype_code(t: torch.Tensor) -> int:
         return DT_F32
     if t.dtype == torch.bfloat16:
         return DT_BF16
+    if t.dtype == torch.float16:
+        return DT_F16
     raise MorecError(f"unsupported dtype {t.dtype}")
 
 
@@ -273,11 +277,10 @@ def gemm(A, B, C, *, C2=None, bias=None, aux=None, M, N, K, lda, ldb, ldc, ldaux
     lib = load()
     dt = gemm_dtype_code(A)
     assert gemm_dtype_code(B) == dt
-    out_bf16 = 1 if C.dtype == torch.bfloat16 else 0
     with _timed_gemm(2.0 * M * N * K):
         rc = lib.morec_gemm(_ptr(A), _ptr(B), _ptr(C), _ptr(C2), _ptr(bias), _ptr(aux), M, N, K,
                             lda, ldb, ldc, ldaux, int(a_mn), int(b_mn),
-                            dt, out_bf16, epilogue, alpha, int(accumulate), _stream())
+                            dt, dtype_code(C), epilogue, alpha, int(accumulate), _stream())
     _check(rc, "morec_gemm")
 
 
@@ -494,17 +497,24 @@ def scatter_add_rows(src, idx, dst):
     return dst
 
 
-class CastPlan:
-    """persistent bf16 shadows of a fixed set of fp32 tensors + the device table that casts all of them in one launch"""
+# Bumped by every FusedAdamW.step(): the fused optimizer writes parameters through raw pointers, which torch's
+# per-tensor version counters do not see.  Weight-shadow caches (ops.ShadowSet) compare against it.
+PARAM_EPOCH = 0
 
-    def __init__(self, srcs):
+
+class CastPlan:
+    """persistent 16-bit shadows (bf16 or fp16) of a fixed set of fp32 tensors + the device table that casts all of
+    them in one launch"""
+
+    def __init__(self, srcs, dtype=torch.bfloat16):
         import numpy as np
         lib = load()
         lib.morec_cast_chunk_elems.restype = c_int
         chunk = lib.morec_cast_chunk_elems()
         dev = srcs[0].device
         self.key = tuple(t.data_ptr() for t in srcs)
-        self.dst = [torch.empty(t.shape, device=dev, dtype=torch.bfloat16) for t in srcs]
+        self.dtype = dtype
+        self.dst = [torch.empty(t.shape, device=dev, dtype=dtype) for t in srcs]
         n = len(srcs)
         rec = np.zeros(n, dtype=np.dtype([("src", "<u8"), ("dst", "<u8"), ("n", "<i8")], align=True))
         assert rec.itemsize == 24
@@ -518,12 +528,13 @@ class CastPlan:
         self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
         self.start = torch.from_numpy(start).to(dev)
 
-    def matches(self, srcs):
-        return len(srcs) == self.n and all(t.data_ptr() == k for t, k in zip(srcs, self.key))
+    def matches(self, srcs, dtype=torch.bfloat16):
+        return len(srcs) == self.n and dtype == self.dtype and all(t.data_ptr() == k for t, k in zip(srcs, self.key))
 
     def run(self):
-        rc = load().morec_cast_f32_to_bf16_multi(_ptr(self.table), _ptr(self.start), self.n, self.n_chunks, _stream())
-        _check(rc, "morec_cast_f32_to_bf16_multi")
+        rc = load().morec_cast_f32_to_16_multi(_ptr(self.table), _ptr(self.start), self.n, self.n_chunks,
+                                               dtype_code(self.dst[0]), _stream())
+        _check(rc, "morec_cast_f32_to_16_multi")
         return self.dst
 
 
@@ -565,15 +576,17 @@ def act_bwd(dy, aux, mode, out=None):
     return out
 
 
-def cast_f32_to_bf16(src, dst):
-    rc = load().morec_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream())
-    _check(rc, "morec_cast_f32_to_bf16")
+def cast_f32_to_16(src, dst):
+    """fp32 -> bf16 / fp16 (dst.dtype)"""
+    rc = load().morec_cast_f32_to_16(_ptr(src), _ptr(dst), src.numel(), dtype_code(dst), _stream())
+    _check(rc, "morec_cast_f32_to_16")
     return dst
 
 
 class AdamTensor(ctypes.Structure):
-    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p_bf16", c_void_p),
-                ("n", c_int), ("lr", c_float), ("wd", c_float)]
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p16", c_void_p),
+                ("n", c_int), ("lr", c_float), ("wd", c_float), ("beta1", c_float), ("beta2", c_float),
+                ("eps", c_float)]
 
 
 AdamChunk = AdamTensor   # layout check in tests
@@ -585,11 +598,18 @@ def adamw_chunk_elems():
     return h.morec_adamw_chunk_elems()
 
 
-def adamw_multi(table_dev, chunk_start_dev, n_tensors, n_chunks, beta1, beta2, eps, step, inv_scale=None,
-                found_inf=None, check_finite=False):
-    rc = load().morec_adamw_multi(_ptr(table_dev), _ptr(chunk_start_dev), n_tensors, n_chunks, beta1, beta2, eps, step,
-                                  _ptr(inv_scale), _ptr(found_inf), int(check_finite), _stream())
+_EXTRA["morec_adamw_multi"] = 1            # step-counter kernel + update kernel (+1 more with check_finite)
+
+
+def adamw_multi(table_dev, chunk_start_dev, n_tensors, n_chunks, step_dev, grad_scale=None, found_inf=None,
+                check_finite=False, p16_dtype=DT_BF16):
+    """step_dev: device float32 scalar (advanced on the device when the update is applied)"""
+    global _LAUNCHES
+    rc = load().morec_adamw_multi(_ptr(table_dev), _ptr(chunk_start_dev), n_tensors, n_chunks, _ptr(step_dev),
+                                  _ptr(grad_scale), _ptr(found_inf), int(check_finite), int(p16_dtype), _stream())
     _check(rc, "morec_adamw_multi")
+    if check_finite and found_inf is not None:
+        _LAUNCHES += 1
 
 
 class BertLayerFwd(ctypes.Structure):

@@ -19,9 +19,13 @@ def _drop_ctx(training, p_hidden, p_attn):
                        base=next(_call_counter) << 44)
 
 
+COMPUTE_DTYPES = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
 def _adt(module):
-    """activation storage dtype of a compute mode: 'fp32' (3xTF32 parity) and 'tf32' store fp32, 'bf16' stores bf16"""
-    return torch.bfloat16 if getattr(module, "compute_dtype", "fp32") == "bf16" else torch.float32
+    """activation storage dtype of a compute mode: 'fp32' (3xTF32 parity) and 'tf32' store fp32, 'bf16' stores bf16,
+    'fp16' stores IEEE half (the arithmetic of the reference's own torch.cuda.amp.autocast path, run.py:242)"""
+    return COMPUTE_DTYPES[getattr(module, "compute_dtype", "fp32")]
 
 
 def _x3(module):
@@ -36,6 +40,7 @@ class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
         self.apply(self._init_weights)
         self.compute_dtype = "fp32"
         self._qkv_groups = None
+        self._shadows = ops.ShadowSet()
 
     def _fused_qkv(self):
         if self._qkv_groups is None:
@@ -43,6 +48,21 @@ class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
                                                      b.multi_head_attention.w_V.weight])
                                 for b in self.transformer_encoder.transformer_blocks]
         return [g.buffer() for g in self._qkv_groups]
+
+    def _compute_weights(self, wqkv, adt):
+        """16-bit copies of the GEMM weights (4 per block), kept by a ShadowSet (one cast launch, or none at all when
+        the attached FusedAdamW writes them)"""
+        srcs, owners = [], []
+        for buf, b in zip(wqkv, self.transformer_encoder.transformer_blocks):
+            m, f = b.multi_head_attention, b.feed_forward
+            D = m.w_Q.weight.shape[0]
+            srcs += [buf.detach(), m.fc.weight.detach(), f.w_1.weight.detach(), f.w_2.weight.detach()]
+            owners += [[(m.w_Q.weight, 0, D), (m.w_K.weight, D, 2 * D), (m.w_V.weight, 2 * D, 3 * D)],
+                       [(m.fc.weight, 0, m.fc.weight.shape[0])], [(f.w_1.weight, 0, f.w_1.weight.shape[0])],
+                       [(f.w_2.weight, 0, f.w_2.weight.shape[0])]]
+        if not all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in srcs):
+            return None
+        return self._shadows.get(srcs, owners, adt)
 
     def _init_weights(self, module):                # reference: encoders.py:14-21
         if isinstance(module, nn.Embedding):
@@ -59,8 +79,9 @@ class User_Encoder(torch.nn.Module):               # reference: encoders.py:7-28
         B, L, D = input_embs.shape
         adt = _adt(self)
         drop = _drop_ctx(self.training, te.dropout_p, te.dropout_p)
+        wqkv = self._fused_qkv()
         meta = dict(n_blocks=len(te.transformer_blocks), n_heads=te.n_heads, L=L, adt=adt, drop=drop, x3=_x3(self),
-                    wqkv=self._fused_qkv())
+                    wqkv=wqkv, cw=self._compute_weights(wqkv, adt) if adt != torch.float32 else None)
         X = input_embs.reshape(B * L, D)
         if X.dtype != adt:
             X = X.to(adt)

@@ -59,35 +59,59 @@ class Model(torch.nn.Module):
         # Multi-GPU: the text tower averages its own gradients, layer by layer, overlapped with its backward
         # (ops._GradSync); DistributedDataParallel (run.py:148) is told to leave those parameters alone (see the
         # `_ddp_params_and_buffers_to_ignore` property).  Everything else (SASRec, ID embedding) stays with DDP.
-        self._overlap_grad_sync = bool(self.use_modal and getattr(args, "overlap_grad_sync", True))
-        self._ddp_wrapped = False
+        self._overlap_grad_sync = False          # switched on explicitly: enable_overlap_grad_sync()
+        self._grad_sync_suspended = False        # parallel.MorecDDP.no_sync()
 
-    @property
-    def _ddp_params_and_buffers_to_ignore(self):
-        """Read by DistributedDataParallel's constructor (and by nothing else): the text tower's parameters are
-        excluded from DDP's reducer because the tower all-reduces them itself during its backward.  The read also
-        records that this replica IS wrapped by DDP -- a bare Model in a process that merely has torch.distributed
-        initialised must not start collectives of its own."""
-        if not self._overlap_grad_sync:
-            return []
-        self._ddp_wrapped = True
-        return [n for n, _ in self.named_parameters() if n.startswith("bert_encoder.")]
+    def enable_overlap_grad_sync(self, process_group=None):
+        """Call BEFORE wrapping the model in DistributedDataParallel (parallel.wrap_ddp does): the text tower then
+        averages its own gradients layer by layer, overlapped with its backward (ops._GradSync), and DDP is told to
+        leave those parameters alone through the `_ddp_params_and_buffers_to_ignore` attribute its constructor reads.
+        Because DDP no longer broadcasts them at construction, the tower's parameters and buffers are broadcast from
+        rank 0 here.  Without this call the tower's gradients simply go through DDP's reducer like everything else."""
+        import torch.distributed as dist
+        if not (self.use_modal and hasattr(self, "bert_encoder")):
+            return self
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            with torch.no_grad():
+                for t in list(self.bert_encoder.parameters()) + list(self.bert_encoder.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        self._ddp_params_and_buffers_to_ignore = (
+            [n for n, _ in self.named_parameters() if n.startswith("bert_encoder.")]
+            + [n for n, _ in self.named_buffers() if n.startswith("bert_encoder.")])
+        self._overlap_grad_sync = True
+        return self
+
+    def attach_optimizer(self, optimizer):
+        """Let a FusedAdamW write the 16-bit compute copies of the GEMM weights in its update kernel (bf16 / fp16
+        modes), so no separate cast pass runs per step.  Optional: without it the copies are refreshed by one
+        multi-tensor cast launch per forward.  Any other writer of the parameters (load_state_dict, a second
+        optimizer) is detected and falls back to the cast."""
+        from ..optim import FusedAdamW
+        opt = optimizer if isinstance(optimizer, FusedAdamW) else None
+        self.user_encoder._shadows.attach(opt)
+        if self.use_modal and hasattr(self, "bert_encoder"):
+            te = self.bert_encoder.text_encoders['title']
+            if not hasattr(te, "_prep_cache"):
+                te._prep_cache = {}
+            te._prep_cache.setdefault("shadows", ops.ShadowSet()).attach(opt)
 
     def set_compute_dtype(self, name):
-        assert name in ("fp32", "tf32", "bf16")
+        from .encoders import COMPUTE_DTYPES
+        assert name in COMPUTE_DTYPES, name
         self.compute_dtype = name
         self.user_encoder.compute_dtype = name
         if self.use_modal:
             self.bert_encoder.text_encoders['title'].compute_dtype = name
         else:
-            self.id_embedding.out_dtype = torch.bfloat16 if name == "bf16" else torch.float32
+            self.id_embedding.out_dtype = COMPUTE_DTYPES[name]
 
     # -------------------------------------------------------------------------------------------
     def _encode_items(self, ids_flat, sample_items):
         if not self.use_modal:
             return self.id_embedding(sample_items.reshape(-1))
         te = self.bert_encoder
-        te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and self._ddp_wrapped
+        te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and not self._grad_sync_suspended
         cfg = te.text_encoders['title'].bert_model.config
         dropout_on = self.training and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0)
         if self.item_dedup == "always" or (self.item_dedup == "auto" and not dropout_on):
@@ -158,12 +182,13 @@ class Model(torch.nn.Module):
         L = self.max_seq_len
         B = log_mask.size(0)
         D = self.args.embedding_dim
-        adt = torch.bfloat16 if self.compute_dtype == "bf16" else torch.float32
+        from .encoders import COMPUTE_DTYPES
+        adt = COMPUTE_DTYPES[self.compute_dtype]
         ids_all = par.all_gather_small(ids_flat).reshape(-1)                      # [G*C]
         if self.use_modal:
             items_all = par.all_gather_small(sample_items.contiguous()).reshape(G * C, -1)
             te = self.bert_encoder
-            te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and self._ddp_wrapped
+            te.text_encoders['title'].overlap_grad_sync = self._overlap_grad_sync and not self._grad_sync_suspended
             T = self.args.num_words_title
             single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
             if single and items_all.dtype != torch.int64:

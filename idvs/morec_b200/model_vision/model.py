@@ -36,13 +36,14 @@ class Model(_TextModel):
         self.set_compute_dtype(self.compute_dtype)
 
     def set_compute_dtype(self, name):
-        assert name in ("fp32", "tf32", "bf16")
+        from ..model.encoders import COMPUTE_DTYPES
+        assert name in COMPUTE_DTYPES, name
         self.compute_dtype = name
         self.user_encoder.compute_dtype = name
         if self.use_modal:
             self.cv_encoder.compute_dtype = name
         else:
-            self.id_embedding.out_dtype = torch.bfloat16 if name == "bf16" else torch.float32
+            self.id_embedding.out_dtype = COMPUTE_DTYPES[name]
 
     def _encode_items(self, ids_flat, sample_items):
         if not self.use_modal:

@@ -38,13 +38,13 @@ class DropCtx:
 
 
 def _cw(p: torch.Tensor, adt: torch.dtype) -> torch.Tensor:
-    """weight in compute dtype (fp32 params are used in place; bf16 mode makes a shadow copy)"""
+    """weight in compute dtype (fp32 params are used in place; the 16-bit modes make a shadow copy)"""
     p = p.detach()
     if adt == torch.float32:
         return p
-    sh = torch.empty(p.shape, device=p.device, dtype=torch.bfloat16)
+    sh = torch.empty(p.shape, device=p.device, dtype=adt)
     if p.numel() % 4 == 0 and p.is_contiguous():
-        lib.cast_f32_to_bf16(p, sh)
+        lib.cast_f32_to_16(p, sh)
     else:
         sh.copy_(p)
     return sh
@@ -222,7 +222,7 @@ def _layer_struct(meta, l, n_tok, n_seq, H, I, cu, w, small, acts, tmp_h):
     drop, adt = meta["drop"], meta["adt"]
     a = lib.BertLayerFwd()
     a.n_tok, a.n_seq, a.H, a.I, a.n_heads, a.max_len = n_tok, n_seq, H, I, meta["n_heads"], meta["max_len"]
-    a.dtype = 1 if adt == torch.bfloat16 else (2 if meta.get("x3", True) else 0)
+    a.dtype = lib.DT_BF16 if adt == torch.bfloat16 else lib.DT_F16 if adt == torch.float16 else (2 if meta.get("x3", True) else 0)
     a.eps, a.p_hidden, a.p_attn = meta["eps"], drop.p_hidden, drop.p_attn
     a.seed = drop.seed & 0xFFFFFFFFFFFFFFFF
     a.off_attn, a.off_ln1, a.off_ln2 = drop.off(1 + 4 * l), drop.off(2 + 4 * l), drop.off(3 + 4 * l)
@@ -235,6 +235,48 @@ def _layer_struct(meta, l, n_tok, n_seq, H, I, cu, w, small, acts, tmp_h):
 
 
 
+class ShadowSet:
+    """Persistent compute-dtype (bf16 / fp16) copies of a fixed list of fp32 GEMM weights.
+
+    They are refreshed by ONE multi-tensor cast launch (lib.CastPlan) -- or not at all: when a FusedAdamW is attached
+    (Model.attach_optimizer) its update kernel writes the 16-bit copy of every parameter it updates next to the fp32
+    master, so the per-step cast pass over the whole tower (0.23 ms for BERT-base) disappears.  Staleness is tracked
+    two ways: torch's per-tensor version counters (any in-place torch op on a parameter: load_state_dict, another
+    optimizer) and lib.PARAM_EPOCH (raw-pointer updates by FusedAdamW instances that do NOT feed this set)."""
+
+    def __init__(self):
+        self.plan = None
+        self.owners = None
+        self.fresh_epoch = -1
+        self.versions = None
+        self.opt = None            # weakref to the attached FusedAdamW
+
+    def attach(self, opt):
+        import weakref
+        self.opt = weakref.ref(opt) if opt is not None else None
+        self.plan = None           # re-register the shadows with the new optimizer on the next get()
+
+    def _register(self):
+        opt = self.opt() if self.opt is not None else None
+        if opt is None:
+            return
+        for dst, own in zip(self.plan.dst, self.owners):
+            for (p, r0, r1) in own:
+                opt.register_shadow(p, dst if (r0 == 0 and r1 == dst.shape[0]) else dst[r0:r1], self)
+
+    def get(self, srcs, owners, adt):
+        """srcs: fp32 tensors (16-byte aligned, contiguous); owners[i]: [(parameter, row0, row1)] whose storage makes
+        up srcs[i] (the fused QKV weight is three parameters).  Returns the list of 16-bit tensors."""
+        if self.plan is None or not self.plan.matches(srcs, adt):
+            self.plan, self.owners, self.fresh_epoch = lib.CastPlan(srcs, adt), owners, -1
+            self._register()
+        vers = tuple(p._version for own in owners for (p, _, _) in own)
+        if self.fresh_epoch != lib.PARAM_EPOCH or vers != self.versions:
+            self.plan.run()
+            self.fresh_epoch, self.versions = lib.PARAM_EPOCH, vers
+        return self.plan.dst
+
+
 def prepare_tower_weights(wqkv_bufs, flat_params, adt, cache=None):
     """compute-dtype copies of every GEMM weight of the text tower (bf16 mode: 4 per layer + fc).  They do not depend
     on the batch, so the caller issues them BEFORE it waits for the packing plan's device->host copy.  With a `cache`
@@ -243,18 +285,22 @@ def prepare_tower_weights(wqkv_bufs, flat_params, adt, cache=None):
     are overwritten by forward i+1, i.e. a backward must run before the weights change and the next forward starts
     (every training loop does; re-casting unchanged weights writes identical values)."""
     n_layers = (len(flat_params) - 7) // 16
-    srcs = []
+    srcs, owners = [], []
     for l in range(n_layers):
         ps = flat_params[5 + 16 * l: 5 + 16 * (l + 1)]
+        H = ps[0].shape[0]
         srcs += [wqkv_bufs[l].detach(), ps[6].detach(), ps[10].detach(), ps[12].detach()]
+        owners += [[(ps[0], 0, H), (ps[2], H, 2 * H), (ps[4], 2 * H, 3 * H)], [(ps[6], 0, ps[6].shape[0])],
+                   [(ps[10], 0, ps[10].shape[0])], [(ps[12], 0, ps[12].shape[0])]]
     srcs.append(flat_params[-2].detach())
+    owners.append([(flat_params[-2], 0, flat_params[-2].shape[0])])
     if adt == torch.float32:
         out = srcs
     elif cache is not None and all(t.is_contiguous() and t.data_ptr() % 16 == 0 for t in srcs):
-        plan = cache.get("cast_plan")
-        if plan is None or not plan.matches(srcs):
-            plan = cache["cast_plan"] = lib.CastPlan(srcs)
-        out = plan.run()
+        ss = cache.get("shadows")
+        if ss is None:
+            ss = cache["shadows"] = ShadowSet()
+        out = ss.get(srcs, owners, adt)
     else:
         out = [_cw(t, adt) for t in srcs]
     return dict(layers=[tuple(out[4 * l: 4 * l + 4]) for l in range(n_layers)], fc=out[-1])
@@ -281,7 +327,7 @@ class BertTowerFn(torch.autograd.Function):
         dh = H // n_heads
         dev = word.device
         scale = 1.0 / math.sqrt(dh)
-        es = 2 if adt == torch.bfloat16 else 4
+        es = 4 if adt == torch.float32 else 2
         I0 = params[5 + 10].shape[0]
         ws = _ws(_WS_FWD, dev)
         own_ws = ws.acquire(dev, n_tok * es * (n_layers * (6 * H + 2 * I0) + 6 * H) + n_layers * n_tok * 8
@@ -394,7 +440,7 @@ class BertTowerFn(torch.autograd.Function):
         dx2 = None                         # second addend of the running hidden-state gradient (sequencer path)
         use_seq = not lib._GEMM_TIMING
         wsb = _ws(_WS_BWD, dev)
-        es = 2 if adt == torch.bfloat16 else 4
+        es = 4 if adt == torch.float32 else 2
         I = params[5 + 10].shape[0]
         own_b = use_seq and wsb.acquire(dev, n_tok * es * (12 * H + I) + 64 * 256)
         newb = (lambda shape, dtype=adt: wsb.take(shape, dtype)) if own_b else \
@@ -559,8 +605,11 @@ class SasrecFn(torch.autograd.Function):
         blocks = []
         for l in range(n_blocks):
             (wq, wk, wv, fc, g1, b1, w1, bb1, w2, bb2, g2, b2) = params[3 + 12 * l: 3 + 12 * (l + 1)]
-            wqkv = _cw(meta["wqkv"][l], adt)                            # fused [3D, D] (FusedParamGroup)
-            w_fc, w_1, w_2 = _cw(fc, adt), _cw(w1, adt), _cw(w2, adt)
+            if meta.get("cw") is not None:                              # persistent 16-bit shadows (ShadowSet)
+                wqkv, w_fc, w_1, w_2 = meta["cw"][4 * l: 4 * l + 4]
+            else:
+                wqkv = _cw(meta["wqkv"][l], adt)                        # fused [3D, D] (FusedParamGroup)
+                w_fc, w_1, w_2 = _cw(fc, adt), _cw(w1, adt), _cw(w2, adt)
             qkv = lib.linear_fwd(h, wqkv)
             ctxo = torch.empty(R, D, device=dev, dtype=adt)
             lib.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ctxo, key_mask=log_mask, causal=True, n_seq=B,

@@ -27,10 +27,38 @@ import torch.distributed as dist
 from torch.nn.parallel import DistributedDataParallel as DDP
 
 
-def wrap_ddp(model, local_rank):
+class MorecDDP(DDP):
+    """DistributedDataParallel whose no_sync() also suspends the text tower's own layer-wise gradient all-reduce
+    (ops._GradSync), so gradient accumulation behaves as with stock DDP."""
+
+    def no_sync(self):
+        import contextlib
+        outer = super().no_sync()
+        mod = self.module
+
+        @contextlib.contextmanager
+        def ctx():
+            prev = getattr(mod, "_grad_sync_suspended", False)
+            mod._grad_sync_suspended = True
+            try:
+                with outer:
+                    yield
+            finally:
+                mod._grad_sync_suspended = prev
+        return ctx()
+
+
+def wrap_ddp(model, local_rank, overlap_grad_sync=True, **ddp_kwargs):
+    """DDP wrapper of a morec Model (run.py:148).  With overlap_grad_sync the text tower averages its own gradients
+    layer by layer during its backward (Model.enable_overlap_grad_sync) and DDP handles the rest."""
+    if overlap_grad_sync and getattr(model, "use_modal", False) and hasattr(model, "enable_overlap_grad_sync"):
+        model.enable_overlap_grad_sync()
+    kw = dict(find_unused_parameters=False, gradient_as_bucket_view=True, bucket_cap_mb=100)
     # gradient_as_bucket_view avoids one copy of the 462 MB fp32 gradient set per step
-    return DDP(model, device_ids=[local_rank], output_device=local_rank, find_unused_parameters=False,
-               gradient_as_bucket_view=True, bucket_cap_mb=100)
+    kw.update(ddp_kwargs)
+    if local_rank is None or (isinstance(local_rank, str) and local_rank == "cpu"):
+        return MorecDDP(model, **kw)
+    return MorecDDP(model, device_ids=[local_rank], output_device=local_rank, **kw)
 
 
 @dataclass

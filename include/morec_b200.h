@@ -16,10 +16,12 @@
  *            1 = bf16 storage, tcgen05 kind::f16, fp32 accumulate                                   ("bf16")
  *            2 = fp32 storage, error-compensated 3xTF32 on tcgen05 (hi*hi + hi*lo + lo*hi, operands split in
  *                shared memory), fp32-grade results: the PARITY mode checked against the CPU oracle  ("fp32")
- *     element-wise / LayerNorm kernels only distinguish the storage type (0 or 2 = fp32, 1 = bf16).  The attention
- *     entry points take the same three codes: 2 runs the exact-fp32 SIMT kernels (parity mode), 0 / 1 run the
- *     tensor-core kernels (TF32 resp. bf16 mma, fp32 softmax) when the shape is covered (<= 64 tokens with 32- or
- *     64-wide heads, <= 32 tokens with 256-wide heads) and fall back to the SIMT kernels otherwise.
+ *            3 = fp16 storage, tcgen05 kind::f16 on IEEE-half operands, fp32 accumulate              ("fp16":
+ *                the arithmetic of the reference's own CUDA path, torch.cuda.amp.autocast, run.py:242)
+ *     element-wise / LayerNorm kernels only distinguish the storage type (0 or 2 = fp32, 1 = bf16, 3 = fp16).  The
+ *     attention entry points take the same codes: 2 runs the exact-fp32 SIMT kernels (parity mode), 0 / 1 / 3 run
+ *     the tensor-core kernels (TF32 resp. bf16 / fp16 mma, fp32 softmax) when the shape is covered (<= 64 tokens
+ *     with 32- or 64-wide heads, <= 32 tokens with 256-wide heads) and fall back to the SIMT kernels otherwise.
  */
 #ifndef MOREC_B200_H
 #define MOREC_B200_H
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MOREC_ABI_VERSION 1
+#define MOREC_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------------- */
 int morec_abi_version(void);
@@ -49,7 +51,7 @@ int morec_device_sms(void);
  * epilogue: see MOREC_EPI_*.  C2 receives the pre-activation for MOREC_EPI_GELU, the activation derivative for
  * MOREC_EPI_GELU_DGELU (needed by the backward).
  * aux ([M,ldaux], same dtype as the operands) feeds the activation-gradient epilogues.
- * out_bf16 selects the element type of C/C2 (fp32 or bf16).  accumulate requires fp32 C and EPI_LINEAR.
+ * out_dtype selects the element type of C/C2 (0 fp32, 1 bf16, 3 fp16).  accumulate requires fp32 C and EPI_LINEAR.
  */
 enum {
     MOREC_EPI_LINEAR = 0,        /* C = alpha*acc + bias                                                   */
@@ -64,7 +66,7 @@ enum {
     MOREC_EPI_MUL_AUX = 7        /* C = alpha*acc * aux              aux = C2 of MOREC_EPI_GELU_DGELU      */
 };
 int morec_gemm(const void* A, const void* B, void* C, void* C2, const float* bias, const void* aux, int M, int N,
-               int K, int lda, int ldb, int ldc, int ldaux, int a_mn_major, int b_mn_major, int dtype, int out_bf16,
+               int K, int lda, int ldb, int ldc, int ldaux, int a_mn_major, int b_mn_major, int dtype, int out_dtype,
                int epilogue, float alpha, int accumulate, void* stream);
 
 /* ---- LayerNorm with fused residual / position add and dropout ---------------------------------
@@ -174,8 +176,9 @@ int morec_scale_add_rows(const void* x, const void* y, const int32_t* idx, const
 int morec_mean_rows(const void* x, void* out, int n_groups, int rows_per_group, int H, int dtype, void* stream);
 /* out = dy * act'(aux): mode 0 = erf-GELU with aux = pre-activation (encoders.py:70), 1 = ReLU with aux = output */
 int morec_act_bwd(const void* dy, const void* aux, void* out, int64_t n, int mode, int dtype, void* stream);
-int morec_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
-/* the same for many tensors in ONE launch (the bf16 weight shadows of a whole tower): tensors = DEVICE array of
+/* fp32 -> 16-bit storage (dst_dtype 1 = bf16, 3 = fp16) */
+int morec_cast_f32_to_16(const float* src, void* dst, int64_t n, int dst_dtype, void* stream);
+/* the same for many tensors in ONE launch (the 16-bit weight shadows of a whole tower): tensors = DEVICE array of
  * n_tensors MorecCastTensor, chunk_start = DEVICE int32[n_tensors+1] exclusive prefix sum of
  * ceil(n / morec_cast_chunk_elems()); src / dst 16-byte aligned. */
 typedef struct MorecCastTensor {
@@ -184,31 +187,36 @@ typedef struct MorecCastTensor {
     long long n;
 } MorecCastTensor;
 int morec_cast_chunk_elems(void);
-int morec_cast_f32_to_bf16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
-                                 void* stream);
+int morec_cast_f32_to_16_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks,
+                               int dst_dtype, void* stream);
 
 /* ---- multi-tensor AdamW with fused unscale + found-inf (run.py:159-162, 245-247) ---------------
  * tensors: DEVICE array of n_tensors MorecAdamTensor (one per parameter); chunk_start: DEVICE int32[n_tensors+1],
  * exclusive prefix sum of ceil(n / morec_adamw_chunk_elems()) per tensor; n_chunks = chunk_start[n_tensors].
- * torch.optim.AdamW semantics (decoupled weight decay, bias correction with `step` >= 1).  inv_scale (device
- * scalar, may be null) multiplies the gradients (GradScaler.unscale_); when check_finite != 0 found_inf (device
- * scalar, zeroed by the caller) is set to 1 if any gradient is inf/nan and the whole update is skipped.
- * p_bf16 (optional) receives a bf16 copy of the updated parameter (bf16-mode weight shadows).
+ * torch.optim.AdamW semantics (decoupled weight decay, bias correction), hyper-parameters PER TENSOR (param groups
+ * may differ in lr / weight decay / betas / eps).  The step count lives on the DEVICE (`step`, float32 scalar like
+ * torch's state['step']): it is advanced by one -- and the update applied -- only when no overflow was found, which
+ * is GradScaler's rule (run.py:245-247) without a host round trip.  grad_scale (device scalar S, may be null):
+ * every gradient is divided by S (GradScaler.unscale_); found_inf (device scalar, may be null): non-zero skips the
+ * update; when check_finite != 0 found_inf (zeroed by the caller) is first set to 1 if any gradient is inf/nan.  p16 (optional) receives a 16-bit copy (p16_dtype 1 = bf16,
+ * 3 = fp16) of the updated parameter: the compute-dtype weight shadow the next forward reads.
  */
 typedef struct MorecAdamTensor {
     float* p;
     const float* g;
     float* m;
     float* v;
-    void* p_bf16;
+    void* p16;
     int n;
     float lr;
     float wd;
+    float beta1;
+    float beta2;
+    float eps;
 } MorecAdamTensor;
 int morec_adamw_chunk_elems(void);
-int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks, float beta1,
-                      float beta2, float eps, int step, const float* inv_scale, float* found_inf, int check_finite,
-                      void* stream);
+int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks, float* step,
+                      const float* grad_scale, float* found_inf, int check_finite, int p16_dtype, void* stream);
 
 /* ---- SM clock probe: out[0] = SM cycles, out[1] = nanoseconds elapsed over a ~20 us spin of one thread; lets
  * bench.py report the SM clock under load without NVML queries inside the timed region (they stall launches). */

@@ -148,6 +148,13 @@ def run_oracle(c, model, d):
     return out, grads
 
 
+def is_null_gradient(name):
+    """The key-projection bias of softmax attention has an EXACTLY zero gradient: q.(k + b) = q.k + q.b adds the same
+    constant to every key of a query, which softmax ignores.  The reference's value for it is rounding noise (~1e-9 of
+    its neighbours), so relative error is meaningless; it is only required to stay negligible."""
+    return name.endswith("attention.self.key.bias")
+
+
 def compare_to_golden(g, loss, score_embs, grads, nonpad, *, loss_tol, emb_tol, grad_tol):
     """loss / item embeddings / every parameter gradient (strided sample + L2 norm) against the reference fixture;
     returns the list of violations (empty = pass).  grad_tol is relative to the reference tensor's max-abs."""
@@ -164,6 +171,11 @@ def compare_to_golden(g, loss, score_embs, grads, nonpad, *, loss_tol, emb_tol, 
             bad.append((k, "missing gradient", None))
             continue
         f = grads[k].detach().double().reshape(-1).cpu()
+        if is_null_gradient(k):
+            lim = 1e-2 * g["grads"][k.replace("key.bias", "query.bias")]["absmax"]
+            if float(f.abs().max()) > lim:
+                bad.append((k, "null gradient too large", float(f.abs().max()), lim))
+            continue
         smp = f[grad_sample_index(f.numel())].float()
         scale = ref["absmax"] + 1e-12
         err = float((smp - ref["sample"]).abs().max())

@@ -30,12 +30,12 @@ def test_header_symbols_exported(lib):
     assert len(syms) >= 19
     for s in syms:
         assert hasattr(h, s), f"{s} declared in include/morec_b200.h but not exported"
-    assert h.morec_abi_version() == 1
+    assert h.morec_abi_version() == 2
 
 
 def test_adam_chunk_struct_layout(lib):
-    # MorecAdamChunk: 5 pointers + int + 2 floats = 56 bytes (8-byte aligned)
-    assert ctypes.sizeof(lib.AdamChunk) == 56
+    # MorecAdamTensor: 5 pointers + int + 5 floats = 64 bytes (8-byte aligned)
+    assert ctypes.sizeof(lib.AdamChunk) == 64
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -20,7 +20,8 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("dt,x3,tol", [(torch.float32, True, 5e-5), (torch.float32, False, 2e-3), (torch.bfloat16, False, 1e-4)])
+@pytest.mark.parametrize("dt,x3,tol", [(torch.float32, True, 5e-5), (torch.float32, False, 2e-3), (torch.bfloat16, False, 1e-4),
+                                       (torch.float16, False, 1e-4)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
 def test_gemm_layouts(lib, dt, x3, tol, a_mn, b_mn):
     with lib.fp32_mode(x3):
@@ -70,15 +71,15 @@ def _epilogue_checks(lib, dt, tol):
         assert rel(acc, dy.double() @ w.double() + 1.0) < tol
 
 
-@pytest.mark.parametrize("dt,x3", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, False)])
+@pytest.mark.parametrize("dt,x3", [(torch.float32, True), (torch.float32, False), (torch.bfloat16, False), (torch.float16, False)])
 def test_gemm_epilogues_and_wgrad(lib, dt, x3):
-    tol = (2e-5 if x3 else 3e-3) if dt == torch.float32 else 1.5e-2
+    tol = (2e-5 if x3 else 3e-3) if dt == torch.float32 else (1.5e-2 if dt == torch.bfloat16 else 2e-3)
     with lib.fp32_mode(x3):
         _epilogue_checks(lib, dt, tol)
 
 
 @pytest.mark.parametrize("H", [64, 128, 512, 768, 2048])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_layernorm_fwd_bwd(lib, H, dt):
     torch.manual_seed(H)
     M, L = 250, 25
@@ -348,6 +349,79 @@ def test_adamw_multi_matches_torch(lib):
         fo.step()
     for r, m in zip(ref, mine):
         assert torch.allclose(r, m, rtol=1e-5, atol=1e-6)
+    # state layout == torch.optim.AdamW's (checkpoint compatibility, data_utils/utils.py:107-114): the fused optimizer
+    # resumes from torch's state dict and vice versa, bias-correction step included
+    sd_t, sd_f = opt.state_dict(), fo.state_dict()
+    assert set(sd_f["state"][0].keys()) == set(sd_t["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd_f["state"][0]["step"]) == float(sd_t["state"][0]["step"]) == 3.0
+    fo2 = FusedAdamW([{"params": mine[:2], "lr": 1e-2, "weight_decay": 0.1}, {"params": mine[2:], "lr": 3e-3, "weight_decay": 0.0}])
+    fo2.load_state_dict(sd_t)
+    opt2 = torch.optim.AdamW([{"params": ref[:2], "lr": 1e-2, "weight_decay": 0.1}, {"params": ref[2:], "lr": 3e-3, "weight_decay": 0.0}])
+    opt2.load_state_dict(sd_f)
+    gs = [torch.randn_like(p) for p in ps]
+    for r, m, g in zip(ref, mine, gs):
+        r.grad = g.clone()
+        m.grad = g.clone()
+    opt2.step()
+    fo2.step()
+    for r, m in zip(ref, mine):
+        assert torch.allclose(r, m, rtol=1e-5, atol=1e-6)
+    assert float(fo2.state_dict()["state"][0]["step"]) == 4.0
+
+
+def test_adamw_per_group_betas_eps_and_shadows(lib):
+    """hyper-parameters are per group (a second group with other betas / eps is honoured) and registered 16-bit
+    shadows receive the updated parameter from the same kernel"""
+    from idvs.morec_b200.optim import FusedAdamW
+    torch.manual_seed(11)
+    ps = [torch.randn(257, 64, device="cuda"), torch.randn(1000, device="cuda")]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [p.clone().requires_grad_(True) for p in ps]
+    groups = lambda q: [{"params": q[:1], "lr": 1e-2, "betas": (0.8, 0.99), "eps": 1e-6},  # noqa: E731
+                        {"params": q[1:], "lr": 2e-3, "betas": (0.95, 0.9), "eps": 1e-3, "weight_decay": 0.3}]
+    opt, fo = torch.optim.AdamW(groups(ref)), FusedAdamW(groups(mine))
+    for dt in (torch.bfloat16, torch.float16):
+        fo.clear_shadows()
+        sh = [torch.zeros(257, 64, device="cuda", dtype=dt)]
+        fo.register_shadow(mine[0], sh[0])
+        for _ in range(2):
+            gs = [torch.randn_like(p) for p in ps]
+            for r, m, g in zip(ref, mine, gs):
+                r.grad, m.grad = g.clone(), g.clone()
+            opt.step()
+            fo.step()
+        for r, m in zip(ref, mine):
+            assert torch.allclose(r, m, rtol=1e-5, atol=1e-6)
+        assert torch.equal(sh[0], mine[0].detach().to(dt))
+
+
+def test_adamw_gradscaler_protocol(lib):
+    """scaler.step(FusedAdamW) (run.py:245-247): gradients are unscaled inside the kernel, an overflow skips BOTH the
+    update and the step count on the device (no host wait), and the result equals GradScaler + torch.optim.AdamW"""
+    from idvs.morec_b200.optim import FusedAdamW
+    torch.manual_seed(12)
+    ps = [torch.randn(300, 33, device="cuda"), torch.randn(77, device="cuda")]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [p.clone().requires_grad_(True) for p in ps]
+    opt, fo = torch.optim.AdamW(ref, lr=1e-2), FusedAdamW(mine, lr=1e-2)
+    sc_r, sc_m = torch.amp.GradScaler("cuda", init_scale=1024.0), torch.amp.GradScaler("cuda", init_scale=1024.0)
+    for it in range(4):
+        gs = [torch.randn_like(p) * 1024.0 for p in ps]
+        if it == 1:
+            gs[0][5, 5] = float("inf")                    # overflow step: skipped by both
+        for r, m, g in zip(ref, mine, gs):
+            r.grad, m.grad = g.clone(), g.clone()
+        sc_r.step(opt); sc_r.update()
+        sc_m.step(fo); sc_m.update()
+        assert float(sc_r.get_scale()) == float(sc_m.get_scale())
+        for r, m in zip(ref, mine):
+            assert torch.allclose(r, m, rtol=1e-5, atol=1e-6), it
+    assert float(fo.state_dict()["state"][0]["step"]) == 3.0 == float(opt.state_dict()["state"][0]["step"])
+    # own overflow check (no GradScaler): check_finite computes found_inf in the optimizer's pre-pass
+    before = [m.detach().clone() for m in mine]
+    mine[0].grad = torch.full_like(mine[0], float("nan")); mine[1].grad = torch.zeros_like(mine[1])
+    fo.step(check_finite=True)
+    assert float(fo.last_found_inf) == 1.0 and all(torch.equal(b, m.detach()) for b, m in zip(before, mine))
 
 
 @pytest.mark.parametrize("n_heads,dh,L,bias,n_mask", [(3, 32, 49, True, 4), (2, 64, 128, False, 0), (12, 32, 49, True, 0), (2, 64, 40, False, 0)])
@@ -434,7 +508,7 @@ def test_scale_add_and_mean_rows(lib):
 # rounding), written per test.
 # ---------------------------------------------------------------------------------------------------------------
 def _tc_modes():
-    return [(torch.float32, 3e-3, 6e-3), (torch.bfloat16, 1.2e-2, 2e-2)]
+    return [(torch.float32, 3e-3, 6e-3), (torch.bfloat16, 1.2e-2, 2e-2), (torch.float16, 3e-3, 6e-3)]
 
 
 @pytest.mark.parametrize("dt,tol_f,tol_b", _tc_modes())
@@ -613,11 +687,12 @@ def test_cast_multi_matches_elementwise_cast(lib):
     """one-launch multi-tensor fp32 -> bf16 cast (tower weight shadows) == torch's cast, incl. ragged tails"""
     torch.manual_seed(21)
     srcs = [torch.randn(s, device="cuda") for s in [(2304, 768), (768,), (3, 5), (16385,), (64, 3072), (1,)]]
-    plan = lib.CastPlan(srcs)
-    assert plan.matches(srcs) and not plan.matches(srcs[:-1])
-    for rep in range(2):                                   # persistent shadows are refreshed in place
-        outs = plan.run()
-        for a, b in zip(srcs, outs):
-            assert b.dtype == torch.bfloat16 and b.shape == a.shape and torch.equal(b, a.to(torch.bfloat16))
-        for a in srcs:
-            a.mul_(1.5)
+    for dt in (torch.bfloat16, torch.float16):
+        plan = lib.CastPlan(srcs, dt)
+        assert plan.matches(srcs, dt) and not plan.matches(srcs[:-1], dt)
+        for rep in range(2):                                   # persistent shadows are refreshed in place
+            outs = plan.run()
+            for a, b in zip(srcs, outs):
+                assert b.dtype == dt and b.shape == a.shape and torch.equal(b, a.to(dt))
+            for a in srcs:
+                a.mul_(1.5)

@@ -35,7 +35,7 @@ def _build(seed, N, T, D, L, dev):
     return a, bert
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, use_wrap):
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
     from idvs.morec_b200.model import Model
@@ -51,7 +51,11 @@ def _worker(rank, world, port, q):
         a, bert = _build(5, N, T, D, L, dev)
         model = Model(a, N, True, bert, full["pop_prob"].numpy()).to(dev).eval()
         model.parallel_mode = "global"
-        ddp = DDP(model, device_ids=[rank])
+        if use_wrap:      # tower gradients averaged layer by layer inside its backward (ops._GradSync), rest by DDP
+            from idvs.morec_b200.parallel import wrap_ddp
+            ddp = wrap_ddp(model, rank)
+        else:             # stock DistributedDataParallel exactly as run.py:148 constructs it
+            ddp = DDP(model, device_ids=[rank], output_device=rank, find_unused_parameters=True)
         sl = slice(rank * B, (rank + 1) * B)
         ids, lm = full["ids"][sl].to(dev), full["log_mask"][sl].to(dev)
         items = full["items"].view(world * B, L + 1, -1)[sl].reshape(B * (L + 1), -1).to(dev)
@@ -84,12 +88,13 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_global_mode_two_gpus_equals_single_process():
+@pytest.mark.parametrize("use_wrap", [False, True])
+def test_global_mode_two_gpus_equals_single_process(use_wrap):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, use_wrap)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]

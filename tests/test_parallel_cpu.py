@@ -173,8 +173,9 @@ def test_layerwise_gradient_sync_world2():
     assert all(ok for _, ok in res), res
 
 
-def test_ddp_ignore_list_marks_wrapping():
-    """Model._ddp_params_and_buffers_to_ignore: DDP skips the text tower and the read marks the replica as wrapped"""
+def test_overlap_grad_sync_is_explicit():
+    """the tower's own gradient averaging is switched on explicitly (enable_overlap_grad_sync / parallel.wrap_ddp);
+    a bare Model never starts collectives and attribute introspection has no side effects"""
     import types
     from transformers import BertConfig, BertModel
     from idvs.morec_b200.model import Model
@@ -184,15 +185,20 @@ def test_ddp_ignore_list_marks_wrapping():
                               num_words_title=8, num_words_abstract=0, num_words_body=0, news_attributes=["title"],
                               bert_model_load="bert_tiny", word_embedding_dim=32)
     m = Model(a, 10, True, BertModel(cfg), np.ones(11) / 11)
-    assert m._ddp_wrapped is False
+    import inspect
+    assert m._overlap_grad_sync is False and not hasattr(m, "_ddp_params_and_buffers_to_ignore")
+    inspect.getmembers(m)                                        # introspection must not flip anything
+    assert m._overlap_grad_sync is False and not hasattr(m, "_ddp_params_and_buffers_to_ignore")
+    m.enable_overlap_grad_sync()                                 # (no process group here: nothing to broadcast)
     names = m._ddp_params_and_buffers_to_ignore
-    assert m._ddp_wrapped is True
-    all_names = [n for n, _ in m.named_parameters()]
+    assert m._overlap_grad_sync is True
+    all_names = [n for n, _ in m.named_parameters()] + [n for n, _ in m.named_buffers()]
     assert names and all(n in all_names and n.startswith("bert_encoder.") for n in names)
     assert not any(n.startswith("user_encoder.") for n in names)
     assert "_ddp_params_and_buffers_to_ignore" not in m.state_dict()
-    m_id = Model(a, 10, False, None, np.ones(11) / 11)          # ID tower: nothing to ignore, never marked
-    assert m_id._ddp_params_and_buffers_to_ignore == [] and m_id._ddp_wrapped is False
+    m_id = Model(a, 10, False, None, np.ones(11) / 11)          # ID tower: nothing to ignore
+    m_id.enable_overlap_grad_sync()
+    assert m_id._overlap_grad_sync is False and not hasattr(m_id, "_ddp_params_and_buffers_to_ignore")
 
 
 def test_unique_first_matches_numpy():

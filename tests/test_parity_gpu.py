@@ -112,7 +112,7 @@ def test_training_mode_dropout_runs_and_is_finite(goldens):
     assert losses[0] != losses[1]          # different dropout masks per call
 
 
-@pytest.mark.parametrize("mode,loss_tol,cos_min", [("tf32", 1e-2, 0.999), ("bf16", 5e-2, 0.95)])
+@pytest.mark.parametrize("mode,loss_tol,cos_min", [("tf32", 1e-2, 0.999), ("bf16", 5e-2, 0.95), ("fp16", 1e-2, 0.999)])
 @pytest.mark.parametrize("name", ["id_cfg1_shape", "text_tiny"])
 def test_fast_modes_stay_close_to_reference(goldens, name, mode, loss_tol, cos_min):
     """fast modes are NOT the parity mode: their measured deviation from the reference is bounded here and reported
@@ -281,7 +281,7 @@ def test_bert_base_all_gradients_vs_oracle():
     assert abs(loss - float(out.loss)) <= 1e-3
     worst = ("", 0.0)
     for k, gr in gref.items():
-        if "pooler" in k:
+        if "pooler" in k or RC.is_null_gradient(k):       # (key bias: exactly-zero gradient, checked by the golden test)
             continue
         assert k in grads, k
         rel = float((grads[k] - gr).abs().max()) / (float(gr.abs().max()) + 1e-12)

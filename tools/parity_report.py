@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_modes.json"))
     ap.add_argument("--cases", default="bert_base_b4,bert_tiny_t128_b16,swin_t_b2")
-    ap.add_argument("--modes", default="fp32,tf32,bf16")
+    ap.add_argument("--modes", default="fp32,tf32,bf16,fp16")
     a = ap.parse_args()
     rep = {}
     for name in a.cases.split(","):
@@ -51,8 +51,9 @@ def main():
             E = cap["E"].detach().float().cpu()
             num = da = db = 0.0
             worst_l2, worst_max = ("", 0.0), ("", 0.0)
+            per = []
             for k, gr in gref.items():
-                if "pooler" in k:
+                if "pooler" in k or RC.is_null_gradient(k):
                     continue
                 g = dict(model.named_parameters())[k].grad.detach().float().cpu().double()
                 gr = gr.double()
@@ -60,17 +61,19 @@ def main():
                 num += float((g * gr).sum()); da += float((g * g).sum()); db += float((gr * gr).sum())
                 l2 = float(diff.norm()) / (float(gr.norm()) + 1e-30)
                 mx = float(diff.abs().max()) / (float(gr.abs().max()) + 1e-30)
+                per.append((round(l2, 5), k))
                 if l2 > worst_l2[1]:
                     worst_l2 = (k, l2)
                 if mx > worst_max[1]:
                     worst_max = (k, mx)
             tot = sum(float(((dict(model.named_parameters())[k].grad.detach().float().cpu().double() - gr.double()) ** 2).sum())
-                      for k, gr in gref.items() if "pooler" not in k)
+                      for k, gr in gref.items() if "pooler" not in k and not RC.is_null_gradient(k))
             rep[name][mode] = dict(loss=float(loss), loss_oracle=float(out.loss), loss_err=abs(float(loss) - float(out.loss)),
                                    emb_max_err=float((E[nonpad] - out.score_embs.detach()[nonpad]).abs().max()),
                                    emb_absmax=float(out.score_embs.detach().abs().max()),
                                    grad_rel_l2=(tot ** 0.5) / (db ** 0.5 + 1e-30), grad_cos=num / ((da * db) ** 0.5 + 1e-30),
-                                   worst_tensor_rel_l2=worst_l2, worst_tensor_rel_max=worst_max)
+                                   worst_tensor_rel_l2=worst_l2, worst_tensor_rel_max=worst_max,
+                                   worst8=sorted(per, reverse=True)[:8])
             print(name, mode, json.dumps(rep[name][mode]), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rep, open(a.out, "w"), indent=1)
