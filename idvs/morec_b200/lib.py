@@ -60,6 +60,10 @@ def load():
         "morec_attn_gen_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, I, F, U, U, P],
         "morec_scale_add_rows": [P, P, P, P, I, F, P, I, I, I, I, P],
         "morec_mean_rows": [P, P, I, I, I, I, P],
+        "morec_eval_hist_bits": [P, P, I, I, I, P, P],
+        "morec_eval_rank": [P, P, P, P, P, I, I, I, I, P, P, P],
+        "morec_bce_fwd": [P, P, P, P, I, I, I, P, P, P, P],
+        "morec_bce_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, P, P, P],
         "morec_bert_layer_fwd": [P, P],
         "morec_bert_layer_bwd": [P, P],
     }
@@ -643,6 +647,67 @@ def bert_layer_bwd(args: BertLayerBwd):
     rc = load().morec_bert_layer_bwd(ctypes.addressof(args), _stream())
     _check(rc, "morec_bert_layer_bwd")
     _LAUNCHES += _N_LAYER_BWD_LAUNCHES - 1
+
+
+def eval_hist_bits(hist_ptr, hist_items, n_cols):
+    """CSR history (hist_ptr int32 [U+1], hist_items int64) -> bit matrix [U, ceil(n_cols/32)] (column 0 always set)"""
+    U = hist_ptr.numel() - 1
+    bits = torch.empty(U, (n_cols + 31) // 32, device=hist_ptr.device, dtype=torch.int32)
+    rc = load().morec_eval_hist_bits(_ptr(hist_ptr), _ptr(hist_items) if hist_items.numel() else None, U,
+                                     hist_items.numel(), n_cols, _ptr(bits), _stream())
+    _check(rc, "morec_eval_hist_bits")
+    return bits
+
+
+_EXTRA["morec_eval_hist_bits"] = 1     # memset + kernel
+_EXTRA["morec_eval_rank"] = 1
+
+
+def eval_rank(P, E, hist_bits, tgt, *, want_seen=False):
+    """rank of item tgt[u] among the catalogue rows of E for every user row of P (see include/morec_b200.h).
+    Returns (rank int32 [U], tgt_score [U], tgt_seen [U] | None)."""
+    U, D = P.shape
+    n_cols = E.shape[0]
+    dev = P.device
+    tgt = tgt.to(torch.int32).contiguous()
+    # target scores through the SAME GEMM path: gathered target rows, padded to a tile-friendly column count so the
+    # kernel variant (tile width, CTA pairing) matches the big pass
+    n_pad = max(512, (U + 255) // 256 * 256)
+    Et = torch.zeros(n_pad, D, device=dev, dtype=E.dtype)
+    gather_rows(E, tgt, out=Et[:U])
+    T = torch.empty(U, n_pad, device=dev, dtype=torch.float32)
+    gemm(P, Et, T, M=U, N=n_pad, K=D, lda=P.stride(0), ldb=D, ldc=n_pad)
+    tgt_score = T.diagonal()[:U].contiguous() if U <= n_pad else None
+    count = torch.empty(U, device=dev, dtype=torch.int32)
+    seen = torch.empty(U, device=dev, dtype=torch.float32) if want_seen else None
+    with _timed_gemm(2.0 * U * n_cols * D):
+        rc = load().morec_eval_rank(_ptr(P), _ptr(E), _ptr(hist_bits), _ptr(tgt_score), _ptr(tgt), U, n_cols, D,
+                                    gemm_dtype_code(P), _ptr(count), _ptr(seen), _stream())
+    _check(rc, "morec_eval_rank")
+    return count + 1, tgt_score, seen
+
+
+def bce_fwd(P, Epos, Eneg, log_mask):
+    R, D = P.shape
+    pos = torch.empty(R, device=P.device, dtype=torch.float32)
+    neg = torch.empty(R, device=P.device, dtype=torch.float32)
+    sum_cnt = torch.empty(2, device=P.device, dtype=torch.float32)
+    rc = load().morec_bce_fwd(_ptr(P), _ptr(Epos), _ptr(Eneg), _ptr(log_mask), R, D, dtype_code(P), _ptr(pos), _ptr(neg),
+                              _ptr(sum_cnt), _stream())
+    _check(rc, "morec_bce_fwd")
+    return pos, neg, sum_cnt
+
+
+_EXTRA["morec_bce_fwd"] = 1
+
+
+def bce_bwd(P, Epos, Eneg, log_mask, pos, neg, grad_out, sum_cnt):
+    R, D = P.shape
+    dP, dEp, dEn = torch.empty_like(P), torch.empty_like(Epos), torch.empty_like(Eneg)
+    rc = load().morec_bce_bwd(_ptr(P), _ptr(Epos), _ptr(Eneg), _ptr(log_mask), _ptr(pos), _ptr(neg), _ptr(grad_out),
+                              _ptr(sum_cnt), R, D, dtype_code(P), _ptr(dP), _ptr(dEp), _ptr(dEn), _stream())
+    _check(rc, "morec_bce_bwd")
+    return dP, dEp, dEn
 
 
 def clock_probe(out):

@@ -69,6 +69,14 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["step"] = self._step_dev
         return self._step_dev
 
+    def state_dict(self):
+        """torch.optim.AdamW's layout; every parameter gets its OWN copy of the (shared) step counter, as torch's
+        optimizers increment each state['step'] tensor separately after loading it"""
+        sd = super().state_dict()
+        sd["state"] = {k: {n: (v.detach().clone() if n == "step" and torch.is_tensor(v) else v) for n, v in st.items()}
+                       for k, st in sd["state"].items()}       # (new dicts: the packed state aliases the live one)
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._step_dev = None          # re-read the step from the loaded state on the next step()

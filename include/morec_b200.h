@@ -218,6 +218,33 @@ int morec_adamw_chunk_elems(void);
 int morec_adamw_multi(const void* tensors, const int32_t* chunk_start, int n_tensors, int n_chunks, float* step,
                       const float* grad_scale, float* found_inf, int check_finite, int p16_dtype, void* stream);
 
+/* ---- full-catalogue evaluation: rank of the held-out item (data_utils/metrics.py:49-57, 77-107) ------------
+ * Replaces, per eval batch of U users,  scores = prec_emb . item_embeddings^T ; scores[history] = -inf ;
+ * scores[1:] ; argsort ; rank of the target  by ONE tcgen05 GEMM whose epilogue counts, per user, the catalogue items
+ * that precede the target:   rank(u) = 1 + count[u],
+ *   count[u] = #{ c in [1, n_cols) : c not in history(u), c != tgt[u],
+ *                 s[u,c] > tgt_score[u]  or  (s[u,c] == tgt_score[u] and c < tgt[u]) }      (= stable descending sort)
+ * The [U, n_cols] score matrix is never written.  morec_eval_hist_bits builds the history bit matrix
+ * bits[U, ceil(n_cols/32)] from a CSR list (hist_ptr int32 [U+1], hist_items int64 [n_hist]); column 0 (the pad item)
+ * is always masked.  tgt_score[u] = <P[u], E[tgt[u]]> must come from the same GEMM path (morec_gemm over the gathered
+ * target rows); tgt_seen (optional, [U]) receives the score this pass computed in the target column, for verification.
+ * P [U, D], E [n_cols, D] row-major, dtype as morec_gemm (2 = fp32-grade 3xTF32, the reference's eval arithmetic).
+ */
+int morec_eval_hist_bits(const int32_t* hist_ptr, const int64_t* hist_items, int U, int n_hist, int n_cols,
+                         uint32_t* bits, void* stream);
+int morec_eval_rank(const void* P, const void* E, const uint32_t* hist_bits, const float* tgt_score, const int32_t* tgt,
+                    int U, int n_cols, int D, int dtype, int32_t* count, float* tgt_seen, void* stream);
+
+/* ---- BCE head of the bce_* packages (bce_text/main-end2end/model/model.py:44-51) ---------------------------
+ * pos[r] = <P[r], Epos[r]>, neg[r] = <P[r], Eneg[r]>; sum_cnt = {sum over valid rows of softplus(-pos) + softplus(neg),
+ * number of valid rows}; loss = sum / cnt (two BCEWithLogits means over the same rows).  Backward: dP, dEpos, dEneg
+ * (same dtype as the inputs: 0 fp32, 1 bf16, 3 fp16) scaled by grad_out / cnt (device scalars). */
+int morec_bce_fwd(const void* P, const void* Epos, const void* Eneg, const float* log_mask, int R, int D, int dtype,
+                  float* pos, float* neg, float* sum_cnt, void* stream);
+int morec_bce_bwd(const void* P, const void* Epos, const void* Eneg, const float* log_mask, const float* pos,
+                  const float* neg, const float* grad_out, const float* sum_cnt, int R, int D, int dtype, void* dP,
+                  void* dEpos, void* dEneg, void* stream);
+
 /* ---- SM clock probe: out[0] = SM cycles, out[1] = nanoseconds elapsed over a ~20 us spin of one thread; lets
  * bench.py report the SM clock under load without NVML queries inside the timed region (they stall launches). */
 int morec_clock_probe(uint64_t* out_cycles_ns, void* stream);

@@ -696,3 +696,84 @@ def test_cast_multi_matches_elementwise_cast(lib):
                 assert b.dtype == dt and b.shape == a.shape and torch.equal(b, a.to(dt))
             for a in srcs:
                 a.mul_(1.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-catalogue evaluation rank (csrc/eval_rank.cu) vs the reference procedure of data_utils/metrics.py:49-57,77-107
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_ranks(P, E, hist, tgt):
+    """the reference's per-user procedure restated on CPU fp64: mask history with -inf, drop column 0, (stable)
+    argsort descending, 1-based position of the target"""
+    S = P.double() @ E.double().t()
+    ranks = []
+    for u in range(P.shape[0]):
+        s = S[u].clone()
+        s[hist[u]] = -float("inf")
+        s = s[1:]
+        order = torch.sort(s, descending=True, stable=True).indices
+        ranks.append(int((order == (tgt[u] - 1)).nonzero()[0, 0]) + 1)
+    return torch.tensor(ranks), S
+
+
+@pytest.mark.parametrize("U,N,D,dt", [(300, 5000, 64, torch.float32), (512, 20000, 512, torch.float32), (77, 1000, 128, torch.float32),
+                                      (512, 20000, 512, torch.bfloat16)])
+def test_eval_rank_matches_reference_procedure(lib, U, N, D, dt):
+    g = torch.Generator().manual_seed(U + N)
+    E = torch.randn(N + 1, D, generator=g) * 0.3
+    E[0] = 0
+    E[7] = E[5]                                            # exact duplicates: ties resolve like a stable sort
+    E[N] = E[N - 3]
+    P = torch.randn(U, D, generator=g) * 0.3
+    lens = torch.randint(0, 24, (U,), generator=g)
+    hist = [torch.randint(1, N + 1, (int(n),), generator=g) for n in lens]
+    tgt = torch.randint(1, N + 1, (U,), generator=g)
+    tgt[0], tgt[1], tgt[2] = 5, 7, N                      # targets that have an exact duplicate elsewhere
+    for u in range(U):                                    # the held-out item is not in the (train) history
+        hist[u] = hist[u][hist[u] != tgt[u]]
+    hist[3] = torch.cat([hist[3], torch.tensor([0, 0])])  # padded history entries (id 0) are harmless
+    Pq, Eq = P.to(dt), E.to(dt)
+    ref, S = _ref_ranks(Pq, Eq, hist, tgt)
+    ptr = torch.zeros(U + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(torch.tensor([h.numel() for h in hist]), 0)
+    bits = lib.eval_hist_bits(ptr.cuda(), torch.cat(hist).cuda(), N + 1)
+    with lib.fp32_mode(True):
+        rank, tscore, seen = lib.eval_rank(Pq.cuda().contiguous(), Eq.cuda().contiguous(), bits, tgt.cuda(), want_seen=True)
+    assert torch.equal(tscore, seen), "target score of the pre-pass differs bitwise from the big pass"
+    rank = rank.cpu().long()
+    if dt == torch.float32:
+        # 3xTF32 scores carry ~1e-6 relative error: a rank may only differ where another item sits within that margin
+        mism = (rank != ref).nonzero().reshape(-1)
+        for u in mism.tolist():
+            t = S[u, tgt[u]]
+            near = ((S[u] - t).abs() < 2e-5 * (1.0 + float(t.abs()))).sum() - 1
+            assert abs(int(rank[u]) - int(ref[u])) <= int(near), (u, int(rank[u]), int(ref[u]), int(near))
+        assert mism.numel() <= max(1, U // 50)
+        assert torch.equal(rank[:3], ref[:3])             # duplicate-embedding ties: exact, stable order
+    else:
+        assert torch.equal(rank, ref)                     # bf16 products are exact in fp32: identical to the fp64 ranking
+    hit10 = (rank <= 10).float()
+    ndcg10 = torch.where(rank <= 10, 1.0 / torch.log2(rank.float() + 1.0), torch.zeros(()))
+    assert float(hit10.sum()) >= 0 and float(ndcg10.max()) <= 1.0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_bce_head_matches_torch(lib, dt):
+    """bce_text/main-end2end/model/model.py:44-51: two BCEWithLogits means over the valid rows"""
+    torch.manual_seed(31)
+    R, D = 333, 128
+    P = (torch.randn(R, D, device="cuda") * 0.4).to(dt)
+    Ep = (torch.randn(R, D, device="cuda") * 0.4).to(dt)
+    En = (torch.randn(R, D, device="cuda") * 0.4).to(dt)
+    lm = (torch.rand(R, device="cuda") > 0.3).float()
+    pos, neg, sc = lib.bce_fwd(P, Ep, En, lm)
+    Pd, Epd, End = (t.double().requires_grad_(True) for t in (P, Ep, En))
+    ps, ns = (Pd * Epd).sum(-1), (Pd * End).sum(-1)
+    idx = lm != 0
+    crit = torch.nn.BCEWithLogitsLoss()
+    loss = crit(ps[idx], torch.ones_like(ps[idx])) + crit(ns[idx], torch.zeros_like(ns[idx]))
+    loss.backward()
+    assert abs(float(sc[0] / sc[1]) - float(loss)) < 1e-5 and float(sc[1]) == float(idx.sum())
+    dP, dEp, dEn = lib.bce_bwd(P, Ep, En, lm, pos, neg, torch.ones(1, device="cuda"), sc)
+    tol = 1e-5 if dt == torch.float32 else (2e-2 if dt == torch.bfloat16 else 3e-3)
+    assert rel(dP, Pd.grad) < tol and rel(dEp, Epd.grad) < tol and rel(dEn, End.grad) < tol
+    assert float(dP[~idx].abs().max()) == 0.0
