@@ -11,6 +11,7 @@ What changed underneath:
 rank(u) = 1 + #{items not in history(u) scoring above the target} (ties as in a stable descending sort).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -55,8 +56,15 @@ def get_item_embeddings(model, item_content, test_batch_size, args, use_modal, l
     try:
         if not use_modal:
             return m.id_embedding.weight.detach().to(torch.float32).clone()
-        content = torch.as_tensor(np.asarray(item_content)).to(dev)
-        n = content.shape[0]
+        store = txn = None
+        if isinstance(item_content, dict):            # vision, real data: {item id: LMDB key} (V/data_utils/metrics.py:64-77)
+            from .vision_data import ImageStore
+            store = ImageStore(os.path.join(args.root_data_dir, args.dataset, args.lmdb_data), args.CV_resize)
+            txn = store.env.begin()
+            n = len(item_content) + 1
+        else:
+            content = item_content if torch.is_tensor(item_content) else torch.as_tensor(np.asarray(item_content))
+            n = content.shape[0]
         share = (n + world - 1) // world
         lo, hi = min(rank * share, n), min((rank + 1) * share, n)
         D = args.embedding_dim
@@ -64,7 +72,13 @@ def get_item_embeddings(model, item_content, test_batch_size, args, use_modal, l
         enc = m.bert_encoder if hasattr(m, "bert_encoder") else m.cv_encoder
         for s in range(lo, hi, test_batch_size):
             e = min(s + test_batch_size, hi)
-            mine[s - lo:e - lo] = enc(content[s:e].long() if content.dtype != torch.float32 else content[s:e]).float()
+            if store is not None:
+                x = torch.stack([store.get(txn, item_content[i]) if i > 0 else torch.zeros(3, args.CV_resize, args.CV_resize)
+                                 for i in range(s, e)]).to(dev)
+            else:
+                x = content[s:e].to(dev)
+                x = x.float() if x.is_floating_point() else x.long()
+            mine[s - lo:e - lo] = enc(x).float()
         if world == 1:
             return mine[:n]
         table = torch.empty(world * share, D, device=dev, dtype=torch.float32)

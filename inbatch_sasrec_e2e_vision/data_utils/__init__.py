@@ -25,29 +25,5 @@ def get_itemId_embeddings(model, item_num, test_batch_size, args, local_rank):
 def get_itemLMDB_embeddings(model, item_num, item_id_to_keys, lmdb_data, test_batch_size, args, local_rank):
     """image tower (data_utils/metrics.py:64-77): every catalogue image through model.module.cv_encoder, sharded over
     the ranks; images are read from the LMDB store batch by batch"""
-    import torch
-    import torch.distributed as dist
-    store = ImageStore(os.path.join(args.root_data_dir, args.dataset, lmdb_data), args.CV_resize)
-    m = model.module if hasattr(model, "module") else model
-    m.eval()
-    dev = torch.device("cuda", local_rank)
-    on = dist.is_available() and dist.is_initialized()
-    rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
-    n = item_num + 1
-    share = (n + world - 1) // world
-    lo, hi = min(rank * share, n), min((rank + 1) * share, n)
-    mine = torch.zeros(share, args.embedding_dim, device=dev)
-    prev = m.compute_dtype
-    m.set_compute_dtype(getattr(args, "eval_dtype", "fp32"))
-    with torch.no_grad(), store.env.begin() as txn:
-        for s in range(lo, hi, test_batch_size):
-            e = min(s + test_batch_size, hi)
-            imgs = torch.stack([store.get(txn, item_id_to_keys[i]) if i > 0 else torch.zeros(3, args.CV_resize, args.CV_resize)
-                                for i in range(s, e)])
-            mine[s - lo:e - lo] = m.cv_encoder(imgs.to(dev)).float()
-    m.set_compute_dtype(prev)
-    if world == 1:
-        return mine[:n]
-    table = torch.empty(world * share, args.embedding_dim, device=dev)
-    dist.all_gather_into_tensor(table, mine)
-    return table[:n].contiguous()
+    args.lmdb_data = lmdb_data
+    return get_item_embeddings(model, item_id_to_keys, test_batch_size, args, True, local_rank)

@@ -287,3 +287,19 @@ def vision_item_encoder(image_net, images: torch.Tensor) -> torch.Tensor:
 # synthetic data of SURVEY.md §8(d): lives in the product package (bench.py uses it too); re-exported here
 # --------------------------------------------------------------------------------------------------
 from idvs.morec_b200.synth import synth_batch  # noqa: E402,F401
+
+
+def bce_model_forward(p: Dict[str, torch.Tensor], sample_items: torch.Tensor, log_mask: torch.Tensor, *, use_modal: bool,
+                      max_seq_len: int, n_heads_user: int, n_heads_bert: int = 0):
+    """Model.forward of the BCE packages (bce_text/main-end2end/model/model.py:30-51) in eval mode: the item tower over
+    every (positive, sampled negative) slot, SASRec over the positives, and two BCE-with-logits means over the valid
+    rows.  sample_items: [B*(L+1)*2, 2T] token rows (modal) or int ids [B, L+1, 2]."""
+    E = text_item_encoder(p, sample_items, n_heads_bert) if use_modal else p["id_embedding.weight"][sample_items.reshape(-1)]
+    D = E.shape[1]
+    E = E.view(-1, max_seq_len + 1, 2, D)
+    pos, neg = E[:, :, 0], E[:, :, 1]
+    prec = sasrec_forward(p, pos[:, :-1], log_mask, n_heads_user)
+    ps = (prec * pos[:, 1:]).sum(-1)
+    ns = (prec * neg[:, :-1]).sum(-1)
+    idx = log_mask != 0
+    return F.softplus(-ps[idx]).mean() + F.softplus(ns[idx]).mean()

@@ -195,3 +195,31 @@ def test_oracle_matches_reference_real_configs(name):
         nonpad = torch.ones_like(nonpad)            # the reference encodes the zero image of a pad slot too
     bad = RC.compare_to_golden(g, out.loss, out.score_embs.detach(), grads, nonpad, loss_tol=2e-5, emb_tol=5e-5, grad_tol=5e-4)
     assert not bad, bad[:10]
+
+
+def test_bce_oracle_matches_reference():
+    """BCE head (bce_text/main-end2end/model/model.py:30-51): the oracle reproduces the unmodified reference's loss
+    and every parameter gradient on a seeded BERT-tiny case (tests/golden/make_golden_bce.py)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_bce as GB
+    import real_cases as RC
+    from idvs.morec_b200.model_bce import Model
+    c = GB.CASE
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "real_bce_tiny.pt"), map_location="cpu", weights_only=False)
+    d = GB.bce_inputs(c)
+    model = GB.build(c, Model)
+    cs = RC.checksums(model.state_dict())
+    assert all(cs[k] == v for k, v in g["weight_checksums"].items())
+    p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in model.state_dict().items()}
+    loss = O.bce_model_forward(p, d["items"], d["log_mask"], use_modal=True, max_seq_len=c["L"], n_heads_user=c["heads"],
+                               n_heads_bert=c["bert_heads"])
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 2e-5
+    for k, ref in g["grads"].items():
+        if "pooler" in k or RC.is_null_gradient(k):
+            continue
+        f = p[k].grad.double().reshape(-1)
+        smp = f[RC.grad_sample_index(f.numel())].float()
+        assert float((smp - ref["sample"]).abs().max()) <= 5e-4 * ref["absmax"] + 1e-7, k
