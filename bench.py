@@ -316,7 +316,8 @@ def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, p
                for i in range(n_batches)]
     a = types.SimpleNamespace(max_seq_len=cfg["L"], embedding_dim=cfg["D"], num_attention_heads=cfg["heads"],
                               drop_rate=cfg["drop"], transformer_block=cfg["blocks"], CV_model_load="swin_tiny")
-    model = Model(a, cfg["N"], True, net, batches[0]["pop_prob"].numpy()).to(dev)
+    from idvs.morec_b200.synth import pop_from_batches
+    model = Model(a, cfg["N"], True, net, pop_from_batches(batches).numpy()).to(dev)
     model.set_compute_dtype(mode)
     model.parallel_mode = "local" if world > 1 else parallel     # (global mode exchanges token rows; images stay local)
     model.train()
@@ -358,9 +359,10 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
         if i in (197, 198):
             p.requires_grad = False
+    from idvs.morec_b200.synth import pop_from_batches
     batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True)
                for i in range(n_batches)]
-    pop = batches[0]["pop_prob"].numpy()
+    pop = pop_from_batches(batches).numpy()       # every in-batch id of every batch has p > 0
     model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
     model.set_compute_dtype(mode)
     model.item_dedup = "always"      # north star: "forward over the batch's unique items" (at every N)
@@ -526,17 +528,21 @@ def main():
     for i in range(2):
         step(*[t.to(dev, non_blocking=True) for t in host[i]])
     sync()
+    e2e_losses = []
     e0.record()
     for i in range(K):
         ids, items, lm = [t.to(dev, non_blocking=True) for t in host[W + i]]
         loss = step(ids, items, lm)
-        _ = float(loss.detach())             # D2H read of the step's loss (also the reference's NaN check, run.py:249)
+        last_loss = float(loss.detach())     # D2H read of the step's loss (also the reference's NaN check, run.py:249)
+        e2e_losses.append(last_loss)
     e1.record()
     sync()
     tms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_value = cfg["B"] * world / (float(tms) / K / 1e3)
+    import math
+    assert all(math.isfinite(v) for v in e2e_losses), f"non-finite training loss in the timed steps: {e2e_losses}"
 
     # ---------------- per-mode throughput (few steps each): makes the cost of the parity mode driver-visible
     modes = None
@@ -603,6 +609,7 @@ def main():
                        "items_encoded": "each distinct non-pad item of the (global) batch once; pad tokens skipped"},
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "host_ms_each_step": step_host_ms,
+            "loss_first_last_e2e": [e2e_losses[0], e2e_losses[-1]] if e2e_losses else None,
             "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline, "modes": modes,
             "cpu_baseline": cpu_base}
     print(json.dumps(line))

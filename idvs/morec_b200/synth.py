@@ -44,7 +44,7 @@ def synth_batch(B: int, L: int, N: int, T: int, seed: int, *, modal: bool, mind_
     pop = counts[1:] / counts[1:].sum()
     pop_prob = np.append([1.0], pop)
     out = dict(ids=torch.from_numpy(ids), log_mask=log_mask_from_ids(torch.from_numpy(ids)),
-               pop_prob=torch.from_numpy(pop_prob))
+               pop_prob=torch.from_numpy(pop_prob), counts=torch.from_numpy(counts))
     if modal:
         content = np.zeros((N + 1, 2 * T), dtype=np.int64)
         lens = g.integers(min(6, T), T + 1, size=N + 1)
@@ -62,3 +62,11 @@ def synth_batch(B: int, L: int, N: int, T: int, seed: int, *, modal: bool, mind_
         out["item_content"] = None
         out["items"] = torch.from_numpy(ids.reshape(-1).copy())
     return out
+
+
+def pop_from_batches(batches):
+    """ONE popularity table for a set of synthetic batches (a model is built with a single pop_prob_list): the summed
+    train-split counts of all of them, so every id of every batch has p > 0 (log p finite), p[0] = 1."""
+    counts = sum(b["counts"] for b in batches)
+    pop = counts[1:] / counts[1:].sum()
+    return torch.cat([torch.ones(1, dtype=pop.dtype), pop])

@@ -40,7 +40,8 @@ def _tiny(L=8, D=64, T=12, N=120, drop=0.0, seed=3):
                               num_words_title=T, num_words_abstract=50, num_words_body=50, news_attributes=["title"],
                               bert_model_load="bert_tiny", word_embedding_dim=128)
     batches = [synth_batch(16, L, N, T, seed + i, modal=True, n_users_pop=100, vocab_lo=10, vocab_hi=900) for i in range(4)]
-    model = Model(a, N, True, bert, batches[0]["pop_prob"].numpy())
+    from idvs.morec_b200.synth import pop_from_batches
+    model = Model(a, N, True, bert, pop_from_batches(batches).numpy())
     return a, model, batches
 
 
