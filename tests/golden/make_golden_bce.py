@@ -41,7 +41,7 @@ def bce_inputs(c):
 def build(c, ModelCls):
     net = RC.build_encoder(c)
     torch.manual_seed(c["seed"] + 1)
-    return ModelCls(RC.make_args(c), c["N"], True, net).eval()
+    return RC.portable_reinit(ModelCls(RC.make_args(c), c["N"], True, net).eval(), c["seed"] + 2)
 
 
 if __name__ == "__main__":

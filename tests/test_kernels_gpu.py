@@ -411,6 +411,7 @@ def test_adamw_gradscaler_protocol(lib):
             gs[0][5, 5] = float("inf")                    # overflow step: skipped by both
         for r, m, g in zip(ref, mine, gs):
             r.grad, m.grad = g.clone(), g.clone()
+        sc_r.scale(torch.zeros(1, device="cuda")); sc_m.scale(torch.zeros(1, device="cuda"))   # (lazy scale initialisation)
         sc_r.step(opt); sc_r.update()
         sc_m.step(fo); sc_m.update()
         assert float(sc_r.get_scale()) == float(sc_m.get_scale())
