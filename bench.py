@@ -407,7 +407,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="morec", choices=["morec", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "bf16"), choices=["fp32", "tf32", "bf16", "fp16"])
+    ap.add_argument("--mode", default=os.environ.get("MOREC_MODE", "fp16"), choices=["fp32", "tf32", "bf16", "fp16"],
+                    help="fp16 (default) = the arithmetic of the reference's own loop (autocast + GradScaler, run.py:242-247)")
     ap.add_argument("--no-modes", action="store_true", help="skip the short per-mode throughput block")
     ap.add_argument("--parallel", default="global", choices=["global", "local"],
                     help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")

@@ -198,6 +198,9 @@ def compare_to_golden(g, loss, score_embs, grads, nonpad, *, loss_tol, emb_tol, 
     if e > emb_tol:
         bad.append(("score_embs", e, emb_tol))
     gmax = max(r["absmax"] for r in g["grads"].values())
+    nmax = max(r["norm"] for r in g["grads"].values())
+    # floors: a tensor whose whole gradient is ~1e-5 of the largest one (e.g. q / k of Swin's last single-window
+    # block) is rounding noise of its neighbours; it only has to stay that small
     for k, ref in g["grads"].items():
         if "pooler" in k:
             continue
@@ -213,8 +216,8 @@ def compare_to_golden(g, loss, score_embs, grads, nonpad, *, loss_tol, emb_tol, 
         smp = f[grad_sample_index(f.numel())].float()
         scale = ref["absmax"] + 1e-12
         err = float((smp - ref["sample"]).abs().max())
-        if err > grad_tol * scale + 1e-7:
+        if err > grad_tol * scale + 1e-5 * gmax + 1e-7:
             bad.append((k, "sample", err / scale))
-        if abs(float(f.norm()) - ref["norm"]) > grad_tol * ref["norm"] + 1e-7:
+        if abs(float(f.norm()) - ref["norm"]) > grad_tol * ref["norm"] + 1e-4 * nmax + 1e-7:
             bad.append((k, "norm", float(f.norm()), ref["norm"]))
     return bad

