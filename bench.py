@@ -300,7 +300,7 @@ def _synth_images(ids, seed, dev=None):
     return imgs[inv]
 
 
-def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global"):
+def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global", use_d2h_plan=False):
     import torch
     from transformers import SwinConfig, SwinForImageClassification
     from idvs.morec_b200.model_vision import Model
@@ -345,7 +345,7 @@ def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, p
     return step, host, resident, h2d_bytes
 
 
-def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global"):
+def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel="global", use_d2h_plan=False):
     """model + optimizer + synthetic batches exactly as the reference loop builds them (run.py:127-162);
     returns (step_fn, pinned host batches, device-resident batches, H2D bytes per step)"""
     import torch
@@ -378,15 +378,22 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
                       {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
     model.attach_optimizer(opt)      # 16-bit weight copies are written by the AdamW kernel (no per-step cast pass)
+    model.set_item_content(batches[0]["item_content"])     # static per-item token counts (one catalogue for all batches)
     host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
     resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    host_ids = {}                         # device batch -> its ids as a host array (the data loader had them there)
+    for (hi, _, _), (ri, _, _) in zip(host, resident):
+        host_ids[ri.data_ptr()] = hi.numpy()
     # fp16 storage needs dynamic loss scaling exactly like the reference's autocast loop (run.py:210, 245-247)
     scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 14)
 
-    def step(ids, items, lm):
+    def step(ids, items, lm, ids_host=None):
         opt.zero_grad(set_to_none=True)
-        loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank)
+        if ids_host is None:
+            ids_host = host_ids.get(ids.data_ptr())
+        loss = model_run(ids.view(-1), items.view(-1, items.size(-1)), lm, local_rank,
+                         host_ids=None if use_d2h_plan else ids_host)
         if model.compute_dtype == "fp16":
             scaler.scale(loss).backward()
             scaler.step(opt)         # unscale + overflow skip fused into the AdamW kernel (no host wait)
@@ -415,6 +422,8 @@ def main():
     ap.add_argument("--workload", default="text", choices=["text", "vision"],
                     help="text = SASRec+BERT-base (headline, configs[2]); vision = SASRec+Swin-T (configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--d2h-plan", action="store_true", help="plan each step from a device->host copy of the ids and token "
+                    "counts (one host wait per step) instead of from the ids the host already has")
     ap.add_argument("--cpu-sample-users", type=int, default=4)
     ap.add_argument("--cpu-port", action="store_true", help="reference arm / cpu_baseline: time the oracle port even "
                     "when a copy of the unmodified reference is available")
@@ -464,7 +473,7 @@ def main():
         dist.init_process_group(backend="nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
     step, host, resident, h2d_bytes = (setup_training_vision if vision else setup_training)(
-        cfg, args.mode, W + K, rank, world, local_rank, args.parallel)
+        cfg, args.mode, W + K, rank, world, local_rank, args.parallel, args.d2h_plan)
 
     def sync():
         if world > 1:
@@ -527,13 +536,13 @@ def main():
 
     # ---------------- end to end through the public API: pinned H2D of each batch + D2H of the loss, every step
     for i in range(2):
-        step(*[t.to(dev, non_blocking=True) for t in host[i]])
+        step(*[t.to(dev, non_blocking=True) for t in host[i]], host[i][0].numpy())
     sync()
     e2e_losses = []
     e0.record()
     for i in range(K):
         ids, items, lm = [t.to(dev, non_blocking=True) for t in host[W + i]]
-        loss = step(ids, items, lm)
+        loss = step(ids, items, lm, host[W + i][0].numpy())
         last_loss = float(loss.detach())     # D2H read of the step's loss (also the reference's NaN check, run.py:249)
         e2e_losses.append(last_loss)
     e1.record()

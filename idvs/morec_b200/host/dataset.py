@@ -100,7 +100,7 @@ class DeviceBatcher:
         self.use_modal = use_modal
         self.flat = torch.from_numpy(flat).to(self.device)
         self.ptr = torch.from_numpy(ptr).to(self.device)
-        self.ptr_host = ptr
+        self.flat_host, self.ptr_host = flat, ptr.astype(np.int64)
         self.content = None
         if use_modal:
             self.content = torch.as_tensor(np.asarray(item_content), dtype=torch.int64).to(self.device)   # [N+1, 2T]
@@ -119,6 +119,16 @@ class DeviceBatcher:
         if total > idx.numel():
             idx = torch.cat([idx, idx[:total - idx.numel()]])
         return idx[rank:total:world]
+
+    def host_ids(self, user_idx):
+        """the batch's item ids [B, L+1] as a host array (same arithmetic as batch(), in numpy): lets the model plan
+        the step without a device->host wait (Model.forward(..., host_ids=))"""
+        u = np.asarray(user_idx, dtype=np.int64)
+        start, end = self.ptr_host[u], self.ptr_host[u + 1]
+        n = np.minimum(end - start, self.Lp1)
+        pos = np.arange(self.Lp1, dtype=np.int64)[None, :] - (self.Lp1 - n)[:, None]
+        src = (end - n)[:, None] + pos
+        return np.where(pos >= 0, self.flat_host[np.maximum(src, 0)].astype(np.int64), 0)
 
     def batch(self, user_idx):
         """user_idx: int64 tensor (host or device) -> (sample_items_id [B, L+1], sample_items, log_mask [B, L])"""

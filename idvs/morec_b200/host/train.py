@@ -197,6 +197,8 @@ def train(args, use_modal, local_rank, kind="text", ctx=_Ctx):
     model = Model(args, item_num, use_modal, encoder, pop_prob_list).to(dev)
     model.set_compute_dtype(args.compute_dtype)
     model.parallel_mode = args.parallel_mode
+    if use_modal and kind == "text":
+        model.set_item_content(item_content)       # static per-item token counts: the step needs no device->host wait
 
     checkpoint, ckpt_path, start_epoch, is_early_stop = None, None, 0, True
     if 'None' not in args.load_ckpt_name:
@@ -223,8 +225,8 @@ def train(args, use_modal, local_rank, kind="text", ctx=_Ctx):
                 super().__init__()
                 self.module = m
 
-            def forward(self, *a):
-                return self.module(*a)
+            def forward(self, *a, **k):
+                return self.module(*a, **k)
         model = _Wrap(module)
 
     if use_modal:
@@ -271,14 +273,15 @@ def train(args, use_modal, local_rank, kind="text", ctx=_Ctx):
         if use_device_batches:
             order = batcher.epoch_order(now_epoch, rank, world)
             for s in range(0, order.numel(), args.batch_size):
-                ids, items, lm = batcher.batch(order[s:s + args.batch_size])
+                users = order[s:s + args.batch_size]
+                ids, items, lm = batcher.batch(users)
                 if kind != "text" and use_modal:
                     items = batcher.images[ids.reshape(-1)].float()
-                yield ids, items, lm
+                yield ids, items, lm, batcher.host_ids(users.numpy())
         else:
             train_dl.sampler.set_epoch(now_epoch)
-            for ids, items, lm in train_dl:
-                yield ids.to(dev, non_blocking=True), items.to(dev, non_blocking=True), lm.to(dev, non_blocking=True)
+            for ids, items, lm in train_dl:                   # the DataLoader's ids are host tensors already
+                yield ids.to(dev, non_blocking=True), items.to(dev, non_blocking=True), lm.to(dev, non_blocking=True), ids
 
     for ep in range(args.epoch):
         now_epoch = start_epoch + ep + 1
@@ -287,7 +290,7 @@ def train(args, use_modal, local_rank, kind="text", ctx=_Ctx):
         Log_file.info('')
         loss, batch_index, need_break = torch.zeros((), device=dev), 1, False
         model.train()
-        for sample_items_id, sample_items, log_mask in batches(now_epoch):
+        for sample_items_id, sample_items, log_mask, host_ids in batches(now_epoch):
             if kind == "text":
                 sample_items = sample_items.view(-1, sample_items.size(-1)) if use_modal else sample_items.view(-1)
             elif use_modal:
@@ -297,7 +300,7 @@ def train(args, use_modal, local_rank, kind="text", ctx=_Ctx):
             sample_items_id = sample_items_id.view(-1)
 
             optimizer.zero_grad(set_to_none=True)
-            bz_loss = model(sample_items_id, sample_items, log_mask, local_rank)
+            bz_loss = model(sample_items_id, sample_items, log_mask, local_rank, host_ids=host_ids)
             loss += bz_loss.detach().float()
             scaler.scale(bz_loss).backward()
             scaler.step(optimizer)

@@ -96,6 +96,16 @@ class Model(torch.nn.Module):
                 te._prep_cache = {}
             te._prep_cache.setdefault("shadows", ops.ShadowSet()).attach(opt)
 
+    def set_item_content(self, item_content):
+        """Tell the model the catalogue's token table (`item_content` [N+1, 2T]: T ids || T attention mask, the array
+        run.py:93-98 builds).  Only the per-item real-token count is kept (host numpy [N+1]): it is a static property
+        of the catalogue, so when the caller also passes the batch's ids as a host array (forward(..., host_ids=))
+        the packed-token layout of a step is planned entirely on the host and the step contains NO device->host wait."""
+        c = item_content.detach().cpu().numpy() if torch.is_tensor(item_content) else np.asarray(item_content)
+        T = self.args.num_words_title
+        self._item_lens = (c[:, T:2 * T] != 0).sum(axis=1).astype(np.int32)
+        return self
+
     def set_compute_dtype(self, name):
         from .encoders import COMPUTE_DTYPES
         assert name in COMPUTE_DTYPES, name
@@ -107,7 +117,18 @@ class Model(torch.nn.Module):
             self.id_embedding.out_dtype = COMPUTE_DTYPES[name]
 
     # -------------------------------------------------------------------------------------------
-    def _encode_items(self, ids_flat, sample_items):
+    def _host_plan_inputs(self, ids_flat, host_ids, n_slots):
+        """(ids, per-slot token counts) as host arrays WITHOUT touching the device, or None"""
+        lens = getattr(self, "_item_lens", None)
+        if host_ids is None or lens is None:
+            return None
+        ids_np = host_ids.detach().cpu().numpy() if torch.is_tensor(host_ids) else np.asarray(host_ids)
+        ids_np = ids_np.reshape(-1).astype(np.int64, copy=False)
+        if ids_np.size != n_slots:
+            raise ValueError(f"host_ids has {ids_np.size} entries, the batch has {n_slots} slots")
+        return ids_np, lens[ids_np]
+
+    def _encode_items(self, ids_flat, sample_items, host_ids=None):
         if not self.use_modal:
             return self.id_embedding(sample_items.reshape(-1))
         te = self.bert_encoder
@@ -121,10 +142,15 @@ class Model(torch.nn.Module):
             single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
             if single and (sample_items.dtype != torch.int64 or sample_items.stride(1) != 1):
                 sample_items = sample_items.to(torch.int64).contiguous()
-            h = lib.d2h_begin([ids_flat, lib.mask_row_lens(sample_items, T)] if single else [ids_flat])
-            prep = te.text_encoders['title'].prepare() if single else None   # weight casts behind the copy, before the wait
-            got = lib.d2h_end(h)
-            ids_np, lens_np = (got[0], got[1]) if single else (got[0], None)
+            hp = self._host_plan_inputs(ids_flat, host_ids, ids_flat.numel()) if single else None
+            if hp is not None:                       # host-side plan: no device->host wait in this step
+                ids_np, lens_np = hp
+                prep = te.text_encoders['title'].prepare()
+            else:
+                h = lib.d2h_begin([ids_flat, lib.mask_row_lens(sample_items, T)] if single else [ids_flat])
+                prep = te.text_encoders['title'].prepare() if single else None   # weight casts behind the copy, before the wait
+                got = lib.d2h_end(h)
+                ids_np, lens_np = (got[0], got[1]) if single else (got[0], None)
             nz = np.nonzero(ids_np)[0]
             from ..parallel import unique_first
             _, first, inv = unique_first(ids_np[nz])
@@ -134,9 +160,13 @@ class Model(torch.nn.Module):
             s2u = np.full(ids_np.size, -1, dtype=np.int32)
             s2u[nz] = inv.astype(np.int32)
             return ops.GatherRowsFn.apply(E_u, lib.h2d(s2u, dev), E_u.dtype)
-        return te(sample_items)
+        hp = self._host_plan_inputs(ids_flat, host_ids, ids_flat.numel()) if len(te.newsname) == 1 else None
+        return te(sample_items, hp[1] if hp is not None else None)
 
-    def forward(self, sample_items_id, sample_items, log_mask, local_rank):
+    def forward(self, sample_items_id, sample_items, log_mask, local_rank, host_ids=None):
+        """The reference's signature (model.py:31) plus one OPTIONAL argument: `host_ids`, the batch's item ids as a
+        host array / CPU tensor (the DataLoader had them on the host anyway).  With it -- and set_item_content() --
+        the step is planned without any device->host synchronisation."""
         if self.parallel_mode == "global" and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             return self._forward_global(sample_items_id, sample_items, log_mask, local_rank)
@@ -149,7 +179,7 @@ class Model(torch.nn.Module):
         B = log_mask.size(0)
         D = self.args.embedding_dim
         log_pop_c = self._log_pop[ids_flat].contiguous()                  # model.py:32-33
-        score_embs = self._encode_items(ids_flat, sample_items)          # [C, D]   model.py:34-37
+        score_embs = self._encode_items(ids_flat, sample_items, host_ids)   # [C, D]   model.py:34-37
         # input_embs[:, :-1]  (model.py:39-41)
         key = (B, L, str(dev))
         if getattr(self, "_in_rows_key", None) != key:

@@ -45,13 +45,16 @@ class Model(_TextModel):
         else:
             self.id_embedding.out_dtype = COMPUTE_DTYPES[name]
 
-    def _encode_items(self, ids_flat, sample_items):
+    def _encode_items(self, ids_flat, sample_items, host_ids=None):
         if not self.use_modal:
             return self.id_embedding(sample_items.reshape(-1))
         # pad slots hold an all-zero image (inbatch_sasrec_e2e_vision/data_utils/dataset.py:86) and never matter:
         # encode each distinct non-pad item once (drop-path is per image, so this is exact in distribution per item)
         dev = ids_flat.device
-        ids_np = lib.d2h_many([ids_flat])[0]
+        if host_ids is not None:                     # the caller had the ids on the host: no device->host wait
+            ids_np = (host_ids.detach().cpu().numpy() if torch.is_tensor(host_ids) else np.asarray(host_ids)).reshape(-1)
+        else:
+            ids_np = lib.d2h_many([ids_flat])[0]
         nz = np.nonzero(ids_np)[0]
         if self.item_dedup == "slots":
             rows = nz

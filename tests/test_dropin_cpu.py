@@ -160,6 +160,7 @@ def test_device_batcher_equals_reference_dataset_and_sampler():
         got = db.batch(users)
         for r, o in zip(ref, got):
             assert r.dtype == o.dtype and torch.equal(r, o)
+        assert np.array_equal(db.host_ids(users.numpy()), ref[0].numpy())
     for world in (1, 2, 4):
         for rank in range(world):
             s = DistributedSampler(range(37), num_replicas=world, rank=rank)

@@ -39,8 +39,8 @@ def run_cuda(model, g):
     cap = {}
     orig = model._encode_items
 
-    def wrapped(ids_flat, items):
-        e = orig(ids_flat, items)
+    def wrapped(ids_flat, items, host_ids=None):
+        e = orig(ids_flat, items, host_ids)
         cap["score_embs"] = e.detach()
         return e
 
@@ -153,7 +153,7 @@ def test_bert_base_shape_vs_oracle():
     model = model.cuda()
     cap = {}
     orig = model._encode_items
-    model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+    model._encode_items = lambda i, x, h=None: cap.setdefault("E", orig(i, x, h))
     loss = model(d["ids"].reshape(-1).cuda(), d["items"].cuda(), d["log_mask"].cuda(), 0)
     assert abs(float(loss) - float(out.loss)) <= 1e-3, (float(loss), float(out.loss))
     nonpad = d["ids"].reshape(-1) != 0
@@ -184,7 +184,7 @@ def test_vision_step_matches_reference_golden(dedup):
     model.item_dedup = dedup
     cap = {}
     orig = model._encode_items
-    model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+    model._encode_items = lambda i, x, h=None: cap.setdefault("E", orig(i, x, h))
     model.zero_grad()
     loss = model(g["ids"].reshape(-1).cuda(), g["images"].cuda(), g["log_mask"].cuda(), 0)
     loss.backward()
@@ -244,7 +244,7 @@ def _run_real(model, d, mode):
     model.set_compute_dtype(mode)
     cap = {}
     orig = model._encode_items
-    model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+    model._encode_items = lambda i, x, h=None: cap.setdefault("E", orig(i, x, h))
     model.zero_grad()
     loss = model(d["ids"].reshape(-1).cuda(), d["items"].cuda(), d["log_mask"].cuda(), 0)
     loss.backward()

@@ -13,8 +13,8 @@ for mode in ("fp32", "bf16"):
     model.set_compute_dtype(mode)
     cap = {}
     orig_enc = model._encode_items
-    def enc(i, x, orig_enc=orig_enc, cap=cap):
-        e = orig_enc(i, x)
+    def enc(i, x, h=None, orig_enc=orig_enc, cap=cap):
+        e = orig_enc(i, x, h)
         cap["E"] = e.detach().float().cpu()
         e.register_hook(lambda gr: cap.__setitem__("dE", gr.detach().float().cpu()))
         return e

@@ -43,7 +43,7 @@ def main():
                 continue
             cap = {}
             orig = model._encode_items
-            model._encode_items = lambda i, x: cap.setdefault("E", orig(i, x))
+            model._encode_items = lambda i, x, h=None: cap.setdefault("E", orig(i, x, h))
             model.zero_grad()
             loss = model(d["ids"].reshape(-1).cuda(), d["items"].cuda(), d["log_mask"].cuda(), 0)
             loss.backward()
