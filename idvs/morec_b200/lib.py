@@ -201,6 +201,7 @@ def gemm_dtype_code(t: torch.Tensor) -> int:
 # synchronises the stream; ~0.3 ms each, measured) and one combined device->host fetch per step
 # ------------------------------------------------------------------------------------------------
 _PIN_RING = []
+_PIN_EVENTS = []       # per slot: event recorded behind the copy that last read it
 _PIN_NEXT = 0
 _PIN_SLOTS = 64
 _PIN_BYTES = 1 << 20
@@ -208,7 +209,9 @@ _PIN_BYTES = 1 << 20
 
 def h2d(arr, device):
     """numpy array -> device tensor through a ring of pinned staging buffers (async, no stream sync).  A slot is
-    reused 64 uploads later; every training step synchronises at least once, long before that."""
+    reused 64 uploads later and is guarded by a CUDA event recorded behind its copy: a step without any host wait
+    lets the host run several steps ahead of the GPU, so the reuse must wait until that copy has really executed
+    (it never blocks unless the host is > 64 uploads ahead)."""
     import numpy as np
     global _PIN_NEXT
     arr = np.ascontiguousarray(arr)
@@ -220,12 +223,21 @@ def h2d(arr, device):
     if not _PIN_RING:
         for _ in range(_PIN_SLOTS):
             _PIN_RING.append(torch.empty(_PIN_BYTES, dtype=torch.uint8).pin_memory())
-    slot = _PIN_RING[_PIN_NEXT]
+            _PIN_EVENTS.append(None)
+    i = _PIN_NEXT
+    slot = _PIN_RING[i]
     _PIN_NEXT = (_PIN_NEXT + 1) % _PIN_SLOTS
+    if _PIN_EVENTS[i] is not None:
+        _PIN_EVENTS[i].synchronize()
     src = torch.from_numpy(arr)
     staged = slot[:nbytes].view(src.dtype).view(arr.shape)
     staged.copy_(src)
-    return staged.to(device, non_blocking=True)
+    out = staged.to(device, non_blocking=True)
+    if out.is_cuda:
+        ev = _PIN_EVENTS[i] if _PIN_EVENTS[i] is not None else torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(out.device))
+        _PIN_EVENTS[i] = ev
+    return out
 
 
 _D2H_BUF = {}
