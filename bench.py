@@ -363,6 +363,10 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True)
                for i in range(n_batches)]
     pop = pop_from_batches(batches).numpy()       # every in-batch id of every batch has p > 0
+    from idvs.morec_b200.synth import synth_catalogue
+    catalogue = synth_catalogue(cfg["N"], cfg["T"], 4242)      # ONE catalogue for every batch and every rank
+    for b in batches:
+        b["items"] = catalogue[b["ids"].reshape(-1)]
     model = Model(make_args(cfg), cfg["N"], True, bert, pop).to(dev)
     model.set_compute_dtype(mode)
     model.item_dedup = "always"      # north star: "forward over the batch's unique items" (at every N)
@@ -378,7 +382,7 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     opt = FusedAdamW([{"params": bert_params, "lr": cfg["fine_tune_lr"], "weight_decay": cfg["fine_tune_l2"]},
                       {"params": rec_params, "lr": cfg["lr"], "weight_decay": cfg["l2"]}])
     model.attach_optimizer(opt)      # 16-bit weight copies are written by the AdamW kernel (no per-step cast pass)
-    model.set_item_content(batches[0]["item_content"])     # static per-item token counts (one catalogue for all batches)
+    model.set_item_content(catalogue)             # static per-item token counts
     host = [(b["ids"].pin_memory(), b["items"].pin_memory(), b["log_mask"].pin_memory()) for b in batches]
     resident = [(a.to(dev), b.to(dev), c.to(dev)) for (a, b, c) in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])

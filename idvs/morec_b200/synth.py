@@ -70,3 +70,20 @@ def pop_from_batches(batches):
     counts = sum(b["counts"] for b in batches)
     pop = counts[1:] / counts[1:].sum()
     return torch.cat([torch.ones(1, dtype=pop.dtype), pop])
+
+
+def synth_catalogue(N: int, T: int, seed: int, vocab_lo: int = 1000, vocab_hi: int = 30000):
+    """ONE synthetic catalogue `item_content` int64 [N+1, 2T] (T token ids || T attention mask, row 0 = pad item): titles
+    of uniform length [6, T] with [CLS]=101 first -- the array run.py:93-98 builds from the news file.  Batches that
+    belong to one run must index the SAME catalogue (an item has one title, on every rank)."""
+    g = np.random.default_rng(seed)
+    content = np.zeros((N + 1, 2 * T), dtype=np.int64)
+    lens = g.integers(min(6, T), T + 1, size=N + 1)
+    tok = g.integers(vocab_lo, vocab_hi, size=(N + 1, T))
+    am = (np.arange(T)[None, :] < lens[:, None]).astype(np.int64)
+    tok = tok * am
+    tok[:, 0] = 101
+    content[:, :T] = tok
+    content[:, T:] = am
+    content[0] = 0
+    return torch.from_numpy(content)
