@@ -102,3 +102,18 @@ extern "C" int morec_bert_layer_bwd(const MorecBertLayerBwd* a, void* stream) {
                    MOREC_EPI_LINEAR, 1.f, 0, stream));
     return MOREC_OK;
 }
+
+// Whole towers per call: `layers` is a HOST array of per-layer argument records (forward: in execution order;
+// backward: in execution order, i.e. last layer first).  One C-ABI transition per pass instead of one per layer -- the
+// host side of a step was as long as its GPU side (bench.py `host_issue_ms_per_step`).
+extern "C" int morec_bert_layers_fwd(const MorecBertLayerFwd* layers, int n_layers, void* stream) {
+    MOREC_CHECK_ARG(layers && n_layers >= 0, "bert_layers_fwd: null args");
+    for (int l = 0; l < n_layers; ++l) RUN(morec_bert_layer_fwd(layers + l, stream));
+    return MOREC_OK;
+}
+
+extern "C" int morec_bert_layers_bwd(const MorecBertLayerBwd* layers, int n_layers, void* stream) {
+    MOREC_CHECK_ARG(layers && n_layers >= 0, "bert_layers_bwd: null args");
+    for (int l = 0; l < n_layers; ++l) RUN(morec_bert_layer_bwd(layers + l, stream));
+    return MOREC_OK;
+}

@@ -64,6 +64,8 @@ def load():
         "morec_eval_rank": [P, P, P, P, P, I, I, I, I, P, P, P],
         "morec_bce_fwd": [P, P, P, P, I, I, I, P, P, P, P],
         "morec_bce_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, P, P, P],
+        "morec_bert_layers_fwd": [P, I, P],
+        "morec_bert_layers_bwd": [P, I, P],
         "morec_bert_layer_fwd": [P, P],
         "morec_bert_layer_bwd": [P, P],
     }
@@ -720,6 +722,38 @@ def bce_bwd(P, Epos, Eneg, log_mask, pos, neg, grad_out, sum_cnt):
                               _ptr(sum_cnt), R, D, dtype_code(P), _ptr(dP), _ptr(dEp), _ptr(dEn), _stream())
     _check(rc, "morec_bce_bwd")
     return dP, dEp, dEn
+
+
+# numpy mirrors of MorecBertLayerFwd / MorecBertLayerBwd (include/morec_b200.h): whole towers are described by ONE
+# structured array filled column-wise (vectorised over layers) and handed to C++ in one call
+import numpy as _np
+
+_FWD_PTRS = ("cu_seqlens", "wqkv", "bqkv", "w_ao", "b_ao", "g1", "b1", "w_i", "b_i", "w_o", "b_o", "g2", "b2", "x", "qkv", "ctx",
+             "tmp_h", "x1", "rstd1", "pre", "act", "x2", "rstd2")
+_BWD_PTRS = ("dy", "dy2", "dz1", "dxq", "dz2", "dbr", "dx1b", "dctx", "dpre", "dqkv", "dwqkv", "dbqkv", "dw_ao", "db_ao", "dg1",
+             "db1", "dw_i", "db_i", "dw_o", "db_o", "dg2", "db2")
+LAYER_FWD_DT = _np.dtype([(n, "<i4") for n in ("n_tok", "n_seq", "H", "I", "n_heads", "max_len", "dtype", "_pad")]
+                         + [(n, "<f4") for n in ("eps", "p_hidden", "p_attn", "_padf")]
+                         + [(n, "<u8") for n in ("seed", "off_attn", "off_ln1", "off_ln2")]
+                         + [(n, "<u8") for n in _FWD_PTRS], align=True)
+LAYER_BWD_DT = _np.dtype([("fwd", LAYER_FWD_DT)] + [(n, "<u8") for n in _BWD_PTRS], align=True)
+assert LAYER_FWD_DT.itemsize == ctypes.sizeof(BertLayerFwd) and LAYER_BWD_DT.itemsize == ctypes.sizeof(BertLayerBwd)
+
+
+def bert_layers_fwd(rec):
+    """rec: numpy array of LAYER_FWD_DT records in execution order"""
+    global _LAUNCHES
+    rc = load().morec_bert_layers_fwd(rec.ctypes.data, rec.shape[0], _stream())
+    _check(rc, "morec_bert_layers_fwd")
+    _LAUNCHES += _N_LAYER_FWD_LAUNCHES * rec.shape[0] - 1
+
+
+def bert_layers_bwd(rec):
+    """rec: numpy array of LAYER_BWD_DT records in execution order (last layer first)"""
+    global _LAUNCHES
+    rc = load().morec_bert_layers_bwd(rec.ctypes.data, rec.shape[0], _stream())
+    _check(rc, "morec_bert_layers_bwd")
+    _LAUNCHES += _N_LAYER_BWD_LAUNCHES * rec.shape[0] - 1
 
 
 def clock_probe(out):

@@ -138,7 +138,12 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
             c["flat"], c["flat_key"] = self._flat_params(), key
         flat = c["flat"]
         wqkv, bqkv = self._fused_qkv()                  # re-validated every call (.to() re-allocates parameters)
-        return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=ops.prepare_tower_weights(wqkv, flat, _adt(self), self._prep_cache))
+        cw = ops.prepare_tower_weights(wqkv, flat, _adt(self), self._prep_cache)
+        lay = c.get("layout")
+        if lay is None or lay.key != ops.TowerLayout.make_key(cw, bqkv) or c.get("layout_flat") is not flat:
+            lay = c["layout"] = ops.TowerLayout(flat, cw, bqkv)      # pointer tables + gradient-arena layout of the sequencer
+            c["layout_flat"] = flat
+        return dict(flat=flat, wqkv=wqkv, bqkv=bqkv, cw=cw, layout=lay)
 
     def forward(self, text, lens_host=None, prep=None):
         """text [n, 2T] int (ids || attention mask) -> [n, D].  Items whose mask is all zero (pad item) return 0.
@@ -178,7 +183,7 @@ class Text_Encoder(torch.nn.Module):                # reference: encoders.py:53-
         drop = _drop_ctx(self.training, cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob)
         meta = dict(n_layers=cfg.num_hidden_layers, n_heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps, max_len=T,
                     adt=adt, drop=drop, x3=_x3(self))
-        meta["wqkv"], meta["bqkv"], meta["cw"] = prep["wqkv"], prep["bqkv"], prep["cw"]
+        meta["wqkv"], meta["bqkv"], meta["cw"], meta["layout"] = prep["wqkv"], prep["bqkv"], prep["cw"], prep.get("layout")
         meta["grad_sync"] = getattr(self, "overlap_grad_sync", False)
         E = ops.BertTowerFn.apply(meta, tok_ids, tok_pos, cu, cls_rows, *prep["flat"])
         if n_enc == n:

@@ -18,6 +18,7 @@ import math
 from dataclasses import dataclass
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import lib
@@ -306,6 +307,70 @@ def prepare_tower_weights(wqkv_bufs, flat_params, adt, cache=None):
     return dict(layers=[tuple(out[4 * l: 4 * l + 4]) for l in range(n_layers)], fc=out[-1])
 
 
+def _al256(n):
+    return (n + 255) // 256 * 256
+
+
+class TowerLayout:
+    """Static description of a text tower for the C++ layer sequencer (lib.bert_layers_fwd / _bwd): device pointers of
+    the weights in compute dtype and of the fp32 biases / LayerNorm parameters (one uint64 row per layer), and the
+    layout of the fp32 gradient arena (fc first, then the layers LAST to FIRST -- the order the backward completes
+    them, so the finished prefix can be all-reduced while the rest is still being computed -- then the embeddings).
+    Built once and cached by Text_Encoder.prepare(); rebuilt when a weight buffer moves."""
+
+    def __init__(self, flat, cw, bqkv):
+        n_layers = (len(flat) - 7) // 16
+        self.n_layers = n_layers
+        self.key = TowerLayout.make_key(cw, bqkv)
+        w = np.zeros((n_layers, 4), dtype=np.uint64)
+        sm = np.zeros((n_layers, 8), dtype=np.uint64)
+        for l in range(n_layers):
+            ps = flat[5 + 16 * l: 5 + 16 * (l + 1)]
+            w[l] = [t.data_ptr() for t in cw["layers"][l]]
+            sm[l] = [bqkv[l].data_ptr()] + [ps[j].data_ptr() for j in (7, 8, 9, 11, 13, 14, 15)]   # b_ao g1 b1 b_i b_o g2 b2
+        self.w, self.sm = w, sm
+        # ---- gradient arena (offsets in floats, every slice 4-float aligned: TMA reduce-add targets)
+        off = 0
+        views = [None] * len(flat)                   # per parameter: (offset, shape)
+
+        def take(shape):
+            nonlocal off
+            o = off
+            off += (math.prod(shape) + 3) // 4 * 4
+            return o
+        H = flat[0].shape[1]
+        views[-2] = (take(flat[-2].shape), tuple(flat[-2].shape))
+        views[-1] = (take(flat[-1].shape), tuple(flat[-1].shape))
+        self.fc_end = off
+        lay = np.zeros((n_layers, 12), dtype=np.int64)        # dwqkv dbqkv dw_ao db_ao dg1 db1 dw_i db_i dw_o db_o dg2 db2
+        self.layer_end = [0] * n_layers
+        for l in reversed(range(n_layers)):
+            base = 5 + 16 * l
+            ps = flat[base: base + 16]
+            o_w, o_b = take((3 * H, H)), take((3 * H,))
+            lay[l, 0], lay[l, 1] = o_w, o_b
+            for j in range(3):
+                views[base + 2 * j] = (o_w + j * H * H, (H, H))
+                views[base + 2 * j + 1] = (o_b + j * H, (H,))
+            for col, j in ((2, 6), (3, 7), (4, 8), (5, 9), (6, 10), (7, 11), (8, 12), (9, 13), (10, 14), (11, 15)):
+                o = take(ps[j].shape)
+                lay[l, col] = o
+                views[base + j] = (o, tuple(ps[j].shape))
+            self.layer_end[l] = off
+        self.lay = lay
+        for i in (3, 4):
+            views[i] = (take(flat[i].shape), tuple(flat[i].shape))
+        views[2] = (take(flat[2].shape), tuple(flat[2].shape))      # token-type table [2, H]: row 0 receives the column sum
+        views[0] = (take(flat[0].shape), tuple(flat[0].shape))
+        views[1] = (take(flat[1].shape), tuple(flat[1].shape))
+        self.views = views
+        self.total = off
+
+    @staticmethod
+    def make_key(cw, bqkv):
+        return tuple(t.data_ptr() for lay in cw["layers"] for t in lay) + (cw["fc"].data_ptr(),) + tuple(b.data_ptr() for b in bqkv)
+
+
 class BertTowerFn(torch.autograd.Function):
     """E[n_seq, D] = GELU(fc(BERT(tokens)[CLS])) over PACKED tokens (pad tokens and pad items are never computed).
 
@@ -344,9 +409,44 @@ class BertTowerFn(torch.autograd.Function):
         del z
         layers = []
         cw = meta.get("cw")                     # weights already in the compute dtype (prepare_tower_weights)
-        use_seq = not lib._GEMM_TIMING          # C++ layer sequencer; the per-kernel path is kept for the roofline leg
-        tmp_h = new((n_tok, H)) if use_seq else None
-        for l in range(n_layers):
+        layout = meta.get("layout")
+        use_seq = not lib._GEMM_TIMING and layout is not None   # C++ layer sequencer; the per-kernel path is kept for the roofline leg
+        seq_saved = None
+        if use_seq:
+            # ONE C-ABI call for all layers: a structured numpy array of per-layer records, filled column-wise
+            I = I0
+            szh, sz3, szi, szr = _al256(n_tok * H * es), _al256(n_tok * 3 * H * es), _al256(n_tok * I * es), _al256(2 * n_tok * 4)
+            block = sz3 + 3 * szh + 2 * szi + szr
+            tmp_h = new((n_tok, H))
+            blk = new((n_layers * block,), torch.uint8)
+            rec = np.zeros(n_layers, dtype=lib.LAYER_FWD_DT)
+            ls = np.arange(n_layers, dtype=np.uint64)
+            b = np.uint64(blk.data_ptr()) + ls * np.uint64(block)
+            rec["n_tok"], rec["n_seq"], rec["H"], rec["I"], rec["n_heads"], rec["max_len"] = n_tok, n_seq, H, I, n_heads, max_len
+            rec["dtype"] = lib.DT_BF16 if adt == torch.bfloat16 else lib.DT_F16 if adt == torch.float16 else (2 if meta.get("x3", True) else 0)
+            rec["eps"], rec["p_hidden"], rec["p_attn"] = eps, drop.p_hidden, drop.p_attn
+            rec["seed"] = np.uint64(drop.seed & 0xFFFFFFFFFFFFFFFF)
+            site = (np.uint64(1) + np.uint64(4) * ls) << np.uint64(36)
+            dbase = np.uint64(drop.base & 0xFFFFFFFFFFFFFFFF)
+            rec["off_attn"], rec["off_ln1"], rec["off_ln2"] = dbase + site, dbase + site + (np.uint64(1) << np.uint64(36)), \
+                dbase + site + (np.uint64(2) << np.uint64(36))
+            rec["cu_seqlens"], rec["tmp_h"] = cu_seqlens.data_ptr(), tmp_h.data_ptr()
+            rec["wqkv"], rec["w_ao"], rec["w_i"], rec["w_o"] = (layout.w[:, j] for j in range(4))
+            for j, nme in enumerate(("bqkv", "b_ao", "g1", "b1", "b_i", "b_o", "g2", "b2")):
+                rec[nme] = layout.sm[:, j]
+            rec["qkv"], rec["ctx"], rec["x1"], rec["x2"] = b, b + np.uint64(sz3), b + np.uint64(sz3 + szh), b + np.uint64(sz3 + 2 * szh)
+            rec["pre"] = b + np.uint64(sz3 + 3 * szh)
+            rec["act"] = rec["pre"] + np.uint64(szi)
+            rec["rstd1"] = rec["act"] + np.uint64(szi)
+            rec["rstd2"] = rec["rstd1"] + np.uint64(4 * n_tok)
+            rec["x"][0] = x.data_ptr()
+            rec["x"][1:] = rec["x2"][:-1]
+            lib.bert_layers_fwd(rec)
+            x0 = x
+            o = (n_layers - 1) * block + sz3 + 2 * szh
+            x = blk[o:o + n_tok * H * es].view(adt).view(n_tok, H)
+            seq_saved = (rec, blk, x0, tmp_h)
+        for l in range(n_layers if not use_seq else 0):
             (qw, qb, kw, kb, vw, vb, aow, aob, g1, b1, iw, ib, ow, ob, g2, b2) = params[5 + 16 * l: 5 + 16 * (l + 1)]
             bqkv = meta["bqkv"][l]                                       # fused [3H] (FusedParamGroup)
             if cw is not None:
@@ -355,32 +455,22 @@ class BertTowerFn(torch.autograd.Function):
                 wqkv = _cw(meta["wqkv"][l], adt)                         # fused [3H, H]
                 w_ao, w_i, w_o = _cw(aow, adt), _cw(iw, adt), _cw(ow, adt)
             I = iw.shape[0]
-            if use_seq:
-                qkv, ctxo, x1, x2 = new((n_tok, 3 * H)), new((n_tok, H)), new((n_tok, H)), new((n_tok, H))
-                pre, act = new((n_tok, I)), new((n_tok, I))
-                rstd = new((2, n_tok), torch.float32)
-                rstd1, rstd2 = rstd[0], rstd[1]
-                small = (bqkv, aob.detach(), g1.detach(), b1.detach(), ib.detach(), ob.detach(), g2.detach(), b2.detach())
-                a = _layer_struct(meta, l, n_tok, n_seq, H, I, cu_seqlens, (wqkv, w_ao, w_i, w_o), small,
-                                  (x, qkv, ctxo, x1, rstd1, pre, act, x2, rstd2), tmp_h)
-                lib.bert_layer_fwd(a)
-            else:
-                qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
-                ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
-                (lib.attn_fwd if max_len <= 32 else lib.attn_gen_fwd)(
-                    qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len,
-                    n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn, seed=drop.seed,
-                    offset=drop.off(1 + 4 * l))
-                ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
-                x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
-                                                 seed=drop.seed, off_pre=drop.off(2 + 4 * l))
-                del ao
-                pre = torch.empty(n_tok, I, device=dev, dtype=adt)
-                act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU_DGELU, pre=pre)   # pre <- gelu'(z)
-                fo = lib.linear_fwd(act, w_o, ob.detach())
-                x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
-                                                 seed=drop.seed, off_pre=drop.off(3 + 4 * l))
-                del fo
+            qkv = lib.linear_fwd(x, wqkv, bqkv)                        # [n_tok, 3H]
+            ctxo = torch.empty(n_tok, H, device=dev, dtype=adt)
+            (lib.attn_fwd if max_len <= 32 else lib.attn_gen_fwd)(
+                qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctxo, cu_seqlens=cu_seqlens, n_seq=n_seq, seqlen=max_len,
+                n_heads=n_heads, head_dim=dh, scale=scale, dropout_p=drop.p_attn, seed=drop.seed,
+                offset=drop.off(1 + 4 * l))
+            ao = lib.linear_fwd(ctxo, w_ao, aob.detach())
+            x1, _, rstd1 = lib.layernorm_fwd(ao, g1.detach(), b1.detach(), eps, residual=x, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(2 + 4 * l))
+            del ao
+            pre = torch.empty(n_tok, I, device=dev, dtype=adt)
+            act = lib.linear_fwd(x1, w_i, ib.detach(), epilogue=lib.EPI_GELU_DGELU, pre=pre)   # pre <- gelu'(z)
+            fo = lib.linear_fwd(act, w_o, ob.detach())
+            x2, _, rstd2 = lib.layernorm_fwd(fo, g2.detach(), b2.detach(), eps, residual=x1, p_pre=drop.p_hidden,
+                                             seed=drop.seed, off_pre=drop.off(3 + 4 * l))
+            del fo
             layers.append([x, qkv, ctxo, x1, rstd1, pre, act, rstd2, (wqkv, w_ao, w_i, w_o)])
             x = x2
         # ---- CLS pooling + fc + GELU
@@ -394,7 +484,7 @@ class BertTowerFn(torch.autograd.Function):
         if own_ws and not torch.is_grad_enabled():
             ws.release()                      # no backward will come (eval / no_grad): nothing stays saved
             ctx.own_ws = False
-        ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre, w_fc=w_fc)
+        ctx.saved = dict(emb=emb_saved, layers=layers, x_last=x, cls=cls, fc_pre=fc_pre, w_fc=w_fc, seq=seq_saved)
         ctx.idx = (tok_ids, tok_pos, cu_seqlens, cls_rows)
         ctx.params = params
         return E
@@ -417,6 +507,8 @@ class BertTowerFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(dh)
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         dE = dE.contiguous().to(adt)
+        if saved.get("seq") is not None:
+            return BertTowerFn._backward_seq(ctx, dE)
         arena = _Arena(dev, [p.shape for p in params] + [(H,)])
         _z = lambda p: arena.take(p.shape)   # noqa: E731  zero-initialised gradient slice
         sync = _GradSync(arena) if _GradSync.enabled(meta) else None
@@ -547,6 +639,101 @@ class BertTowerFn(torch.autograd.Function):
         grads[3] = deg if need[3] else None
         grads[4] = deb if need[4] else None
         if sync:
+            sync.wait()
+        ctx.saved = None
+        if own_b:
+            wsb.release()
+        if getattr(ctx, "own_ws", False):
+            _ws(_WS_FWD, dev).release()
+            ctx.own_ws = False
+        return (None, None, None, None, None) + tuple(grads)
+
+
+    @staticmethod
+    def _backward_seq(ctx, dE):
+        """backward on the C++ layer sequencer: the gradient arena and every per-layer record are laid out by
+        TowerLayout, all layers run in ONE C-ABI call (or one per layer when the layer-wise gradient all-reduce of a
+        multi-GPU run interleaves with them)"""
+        meta, saved, params = ctx.meta, ctx.saved, ctx.params
+        tok_ids, tok_pos, cu_seqlens, cls_rows = ctx.idx
+        n_layers, adt, drop, eps = meta["n_layers"], meta["adt"], meta["drop"], meta["eps"]
+        lay = meta["layout"]
+        rec, blk, x0, _tmp = saved["seq"]
+        need = [p.requires_grad for p in params]
+        word, posw, typew, eg, eb = params[:5]
+        fc_w, fc_b = params[-2:]
+        H = word.shape[1]
+        I = params[5 + 10].shape[0]
+        n_tok = tok_ids.numel()
+        dev = word.device
+        es = 4 if adt == torch.float32 else 2
+        buf = torch.zeros(max(lay.total, 4), device=dev, dtype=torch.float32)     # ONE memset for every parameter gradient
+        abase = buf.data_ptr()
+
+        def view(i):
+            o, shape = lay.views[i]
+            return buf[o:o + math.prod(shape)].view(shape)
+        arena = type("_FlatArena", (), {})()
+        arena.buf, arena.off = buf, 0
+        sync = _GradSync(arena) if _GradSync.enabled(meta) else None
+        # ---- fc + GELU backward
+        cls, fc_pre = saved["cls"], saved["fc_pre"]
+        dpre = lib.act_bwd(dE, fc_pre, 0)
+        lib.linear_wgrad(dpre, cls, view(-2))
+        lib.colsum(dpre, view(-1))
+        if sync:
+            arena.off = lay.fc_end
+            sync.flush()
+        dcls = lib.linear_dgrad(dpre, saved["w_fc"])
+        dx32 = torch.zeros(n_tok, H, device=dev, dtype=torch.float32)
+        lib.scatter_add_rows(dcls, cls_rows, dx32)
+        dx = dx32 if adt == torch.float32 else dx32.to(adt)
+        del dx32
+        # ---- layers, last to first
+        wsb = _ws(_WS_BWD, dev)
+        own_b = wsb.acquire(dev, n_tok * es * (12 * H + I) + 64 * 256)
+        newb = (lambda shape, dtype=adt: wsb.take(shape, dtype)) if own_b else \
+               (lambda shape, dtype=adt: torch.empty(shape, device=dev, dtype=dtype))
+        ws_h = newb((4 if drop.p_hidden > 0 else 3, n_tok, H))   # dz2, dx1b, dctx, (dbr)
+        dpre_ws, dqkv_ws = newb((n_tok, I)), newb((n_tok, 3 * H))
+        pp = [newb((n_tok, H)) for _ in range(4)]                # ping-pong pairs for (dz1, dxq)
+        recb = np.zeros(n_layers, dtype=lib.LAYER_BWD_DT)
+        order = np.arange(n_layers - 1, -1, -1)                  # record k <-> layer order[k]
+        recb["fwd"] = rec[order]
+        recb["fwd"]["tmp_h"] = ws_h[0].data_ptr()
+        par = (order & 1).astype(np.int64)
+        p0, p1, p2, p3 = (t.data_ptr() for t in pp)
+        recb["dz1"] = np.where(par == 0, p0, p2).astype(np.uint64)
+        recb["dxq"] = np.where(par == 0, p1, p3).astype(np.uint64)
+        recb["dy"][0], recb["dy2"][0] = dx.data_ptr(), 0
+        recb["dy"][1:], recb["dy2"][1:] = recb["dz1"][:-1], recb["dxq"][:-1]
+        recb["dz2"], recb["dx1b"], recb["dctx"] = ws_h[0].data_ptr(), ws_h[1].data_ptr(), ws_h[2].data_ptr()
+        recb["dbr"] = ws_h[3].data_ptr() if drop.p_hidden > 0 else 0
+        recb["dpre"], recb["dqkv"] = dpre_ws.data_ptr(), dqkv_ws.data_ptr()
+        g = (np.uint64(abase) + (lay.lay[order] * 4).astype(np.uint64))
+        for j, nme in enumerate(("dwqkv", "dbqkv", "dw_ao", "db_ao", "dg1", "db1", "dw_i", "db_i", "dw_o", "db_o", "dg2", "db2")):
+            recb[nme] = g[:, j]
+        if sync is None:
+            lib.bert_layers_bwd(recb)
+        else:
+            for k in range(n_layers):                            # this layer's gradients: all-reduce while the layers below run
+                lib.bert_layers_bwd(recb[k:k + 1])
+                arena.off = lay.layer_end[int(order[k])]
+                sync.flush()
+        last = int(order[-1]) & 1
+        dx, dx2 = pp[2 * last], pp[2 * last + 1]
+        # ---- embeddings backward: y = dropout(LN(z)), z = word + pos + type
+        y_emb, rstd0 = saved["emb"]
+        dtypew = view(2)
+        dz0, _ = lib.layernorm_bwd(dx, y_emb, eg.detach(), eb.detach(), rstd0, dy2=dx2, dgamma=view(3), dbeta=view(4),
+                                   dbias=dtypew[0], p_post=drop.p_hidden, seed=drop.seed, off_post=drop.off(0))
+        dword = view(0) if need[0] else None
+        dposw = view(1) if need[1] else None
+        if dword is not None or dposw is not None:
+            lib.bert_embed_bwd(dz0, tok_ids, tok_pos, dword, dposw)
+        grads = [view(i) if need[i] else None for i in range(len(params))]
+        if sync:
+            arena.off = lay.total
             sync.wait()
         ctx.saved = None
         if own_b:

@@ -282,6 +282,9 @@ typedef struct MorecBertLayerBwd {
     float* dw_i; float* db_i; float* dw_o; float* db_o; float* dg2; float* db2;
 } MorecBertLayerBwd;
 int morec_bert_layer_bwd(const MorecBertLayerBwd* args, void* stream);
+/* several layers per call: HOST arrays of records in execution order (backward: last layer first) */
+int morec_bert_layers_fwd(const MorecBertLayerFwd* layers, int n_layers, void* stream);
+int morec_bert_layers_bwd(const MorecBertLayerBwd* layers, int n_layers, void* stream);
 
 #ifdef __cplusplus
 }
