@@ -54,7 +54,9 @@ def test_model_module_surface():
     from idvs.morec_b200.model import Model
     from idvs.morec_b200.model import encoders, modules
     assert list(inspect.signature(Model.__init__).parameters)[1:] == ["args", "item_num", "use_modal", "bert_model", "pop_prob_list"]
-    assert list(inspect.signature(Model.forward).parameters)[1:] == ["sample_items_id", "sample_items", "log_mask", "local_rank"]
+    fwd = inspect.signature(Model.forward).parameters
+    assert list(fwd)[1:5] == ["sample_items_id", "sample_items", "log_mask", "local_rank"]          # the reference's call
+    assert all(p.default is not inspect.Parameter.empty for p in list(fwd.values())[5:])        # extras are optional
     for name in ("User_Encoder", "Text_Encoder", "Bert_Encoder"):
         assert hasattr(encoders, name)
     for name in ("TransformerEncoder", "TransformerBlock", "MultiHeadedAttention", "PositionwiseFeedForward"):
