@@ -487,8 +487,12 @@ def main():
     # ---------------- device-resident throughput (`value`): K steps, batches already in HBM
     # warm-up: W steps, the first one on the batch with the most real tokens so the allocator reaches its
     # steady-state footprint before anything is timed
-    big = 0 if vision else max(range(len(host)),
-                               key=lambda i: int((host[i][1].reshape(-1, 2 * cfg["T"])[:, cfg["T"]:] != 0).sum()))
+    if vision:
+        big = 0
+    else:       # packed token count of a step = tokens of the batch's DISTINCT items
+        import numpy as np
+        lens = step.model._item_lens
+        big = max(range(len(host)), key=lambda i: int(lens[np.unique(host[i][0].numpy())].sum()))
     step(*resident[big])
     for i in range(W - 1):
         step(*resident[i])
