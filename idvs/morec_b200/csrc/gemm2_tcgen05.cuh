@@ -18,6 +18,18 @@
 
 namespace morec {
 
+// tools/gemm_trace.cu compiles this header with MOREC_GEMM_TRACE: CTA 0 records clock64() at the hand-over points of
+// its producer / MMA / epilogue warps (no effect on the library build)
+#ifdef MOREC_GEMM_TRACE
+__device__ long long g_gemm_trace[6][4096];
+#define MOREC_TRACE(row, idx)                                                                 \
+    do {                                                                                      \
+        if (blockIdx.x == 0 && (idx) < 4096) g_gemm_trace[row][idx] = clock64();              \
+    } while (0)
+#else
+#define MOREC_TRACE(row, idx) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -41,6 +53,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* desc, uint32_t bar, 
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// ... and additionally written to the same SMEM offset of every CTA in `mask` (cluster ranks); the bytes are credited
+// to the leader of each destination CTA's pair
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
@@ -102,8 +122,11 @@ struct Cfg2 {
 template <class Epi>
 constexpr int gemm2_threads() { return kThreads + (Epi::kGroups == 2 ? 128 : 0); }
 
-template <int KIND, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<Epi>(), 1)
+// CL = cluster size: 2 (one CTA pair) or 4 (two CTA pairs stacked along M that share every B tile: each CTA fetches a
+// QUARTER of the B tile and multicasts it to its counterpart in the other pair, so the cluster reads 96 KB per K-block
+// from L2 instead of 128 KB).  See gemm2_cluster4_enabled() for the measurement that keeps CL = 4 opt-in.
+template <int KIND, class Epi, int CL>
+__global__ void __launch_bounds__(gemm2_threads<Epi>(), 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TileSched p,
              const typename Epi::Params ep) {
@@ -122,7 +145,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    constexpr int PAIRS = CL / 2;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;             // rank within the CTA pair
+    const uint32_t psub = crank >> 1;             // pair within the cluster
+    const uint32_t lead_rank = crank & ~1u;       // cluster rank of this pair's leader
     const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
@@ -134,7 +161,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 2);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), PAIRS);        // every pair that reads the slot commits to it
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
@@ -153,27 +180,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int pair = blockIdx.x >> 1;
-    const int n_pairs = gridDim.x >> 1;
-    const int total_work = p.m_tiles * p.n_tiles * p.splits;      // m_tiles counts 256-row pair tiles here
+    const int pair = blockIdx.x / CL;             // work is dealt to clusters; the pairs of a cluster share (n-tile, split)
+    const int n_pairs = gridDim.x / CL;
+    const int total_work = p.m_tiles * p.n_tiles * p.splits;      // m_tiles counts (PAIRS x 256)-row cluster tiles here
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            [[maybe_unused]] int tr = 0;
             for (int w = pair; w < total_work; w += n_pairs) {
                 const int split = w % p.splits;
                 const int tile = w / p.splits;
-                const int m0 = (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M;
+                const int m0 = ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M;
                 const int n0 = (tile % p.n_tiles) * C::BLOCK_N + (int)rank * C::HALF_N;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    MOREC_TRACE(0, tr); ++tr;
                     const uint32_t fb = smem_u32(&full_bar[stage]);
+#ifdef MOREC_TRACE_NOLOAD          /* diagnostic: MMAs on whatever the ring holds, no operand traffic at all */
+                    if (leader) mbar_arrive(fb);
+                    else mbar_arrive_cluster(fb, lead_rank);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+#endif
                     if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
-                    else mbar_arrive_cluster(fb, 0);
+                    else mbar_arrive_cluster(fb, lead_rank);
                     const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
                     const uint32_t sb = sa + C::A_BYTES;
                     const int k0 = kb * C::BLOCK_K;
@@ -184,12 +219,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         for (int c = 0; c < BLOCK_M / C::CHUNK; ++c)
                             tma_load_2d_2sm(&tmA, fb, sa + c * (C::BLOCK_K * 128), m0 + c * C::CHUNK, k0);
                     }
-                    if (!p.b_mn) {
-                        tma_load_2d_2sm(&tmB, fb, sb, k0, n0);
-                    } else {
+                    if constexpr (CL == 2) {
+                        if (!p.b_mn) {
+                            tma_load_2d_2sm(&tmB, fb, sb, k0, n0);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < C::HALF_N / C::CHUNK; ++c)
-                            tma_load_2d_2sm(&tmB, fb, sb + c * (C::BLOCK_K * 128), n0 + c * C::CHUNK, k0);
+                            for (int c = 0; c < C::HALF_N / C::CHUNK; ++c)
+                                tma_load_2d_2sm(&tmB, fb, sb + c * (C::BLOCK_K * 128), n0 + c * C::CHUNK, k0);
+                        }
+                    } else {
+                        // this CTA's quarter of the B tile -> itself and the CTA of equal pair rank in the other pair
+                        const uint16_t mask = (uint16_t)(0x5u << rank);
+                        constexpr int QROWS = C::HALF_N / PAIRS;                 // 64 N-rows per CTA
+                        if (!p.b_mn) {
+                            tma_load_2d_2sm_mc(&tmB, fb, sb + psub * (QROWS * 128), k0, n0 + (int)psub * QROWS, mask);
+                        } else {
+                            constexpr int NCH = C::HALF_N / C::CHUNK / PAIRS;    // MN-major chunks per CTA
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) {
+                                const int cc = (int)psub * NCH + c;
+                                tma_load_2d_2sm_mc(&tmB, fb, sb + cc * (C::BLOCK_K * 128), n0 + cc * C::CHUNK, k0, mask);
+                            }
+                        }
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -205,16 +256,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        [[maybe_unused]] int tr = 0, trt = 0;
         for (int w = pair; w < total_work; w += n_pairs) {
             const int split = w % p.splits;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
             mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
             tc_fence_after();
+            if (lane == 0) MOREC_TRACE(3, trt);
+            ++trt;
             const uint32_t d_tmem = tmem_base + acc * C::BLOCK_N;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 tc_fence_after();
+                if (lane == 0) MOREC_TRACE(1, tr);
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
                     const uint32_t sb = sa + C::A_BYTES;
@@ -228,9 +283,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                                    : make_smem_desc(sb + k * 32, 16, 1024);
                         tc_mma_2sm<KIND == 1 ? 1 : 0>(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit_2sm_mc(smem_u32(&empty_bar[stage]), 3);            // slot free in both CTAs
-                    if (kb == kb1 - 1) tc_commit_2sm_mc(smem_u32(&tfull_bar[acc]), 3);   // accumulators ready in both
+                    tc_commit_2sm_mc(smem_u32(&empty_bar[stage]), (uint16_t)((1u << CL) - 1));   // slot consumed by this pair: tell every CTA of the cluster
+                    if (kb == kb1 - 1) tc_commit_2sm_mc(smem_u32(&tfull_bar[acc]), (uint16_t)(3u << (2 * psub)));   // accumulators ready in both CTAs of the pair
+                    MOREC_TRACE(2, tr);
                 }
+                ++tr;
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -251,29 +308,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         st.f16 = p.out_f16 != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        [[maybe_unused]] int trt = 0;
         if (pair < total_work) {                            // epilogue side inputs of the first tile -> L2
             const int tile = pair / p.splits;
-            Epi::template prefetch<C::BLOCK_N>(ep, (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
+            Epi::template prefetch<C::BLOCK_N>(ep, ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
                                                (tile % p.n_tiles) * C::BLOCK_N, p);
         }
         for (int w = pair; w < total_work; w += n_pairs) {
             const int split = w % p.splits;
             const int tile = w / p.splits;
-            const int m0 = (tile / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M;
+            const int m0 = ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * C::BLOCK_N;
             if (w + n_pairs < total_work) {                 // ... and of the next tile, one tile time ahead
                 const int nt = (w + n_pairs) / p.splits;
-                Epi::template prefetch<C::BLOCK_N>(ep, (nt / p.n_tiles) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
+                Epi::template prefetch<C::BLOCK_N>(ep, ((nt / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
                                                    (nt % p.n_tiles) * C::BLOCK_N, p);
             }
             Epi::template pre_tile<KIND, C::BLOCK_N>(ep, tmC2, st, m0, q, n0, p, cg, Epi::kGroups);
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
+            if (warp == 4 && lane == 0) MOREC_TRACE(4, trt);
             Epi::template tile<KIND, C::BLOCK_N>(ep, tmC, tmC2, tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::BLOCK_N, st, m0, q,
                                                  n0, split, p, cg, Epi::kGroups);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);    // leader's barrier
+            if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), lead_rank);    // the pair leader's barrier
+            if (warp == 4 && lane == 0) MOREC_TRACE(5, trt);
+            ++trt;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) tma_store_wait<0>();
@@ -288,9 +349,35 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 }
 
+// Cluster size for a problem.  The four-CTA cluster (B multicast) is OPT-IN (MOREC_GEMM_CL4=1): measured on B200 it is
+// 8-30 % SLOWER than the plain CTA pair at every BERT-base shape (12037x3072x768: 59.6 us vs 54.6 us) although its
+// per-CTA cycle trace is identical -- the mainloop is not limited by L2 delivery: with the operand loads removed
+// altogether (tools/gemm_trace.cu, -DMOREC_TRACE_NOLOAD) a K-block still takes 650-700 cycles against 766 with loads,
+// i.e. the SS-mode MMA itself paces the kernel.  Kept for the record and for other shapes.
+inline bool gemm2_cluster4_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOREC_GEMM_CL4");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+template <int KIND, class Epi, int CL>
+int gemm2_launch_cl(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream);
+
 template <int KIND, class Epi>
 int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
+    const int pair_tiles = (g.M + Cfg2<KIND>::PAIR_M - 1) / Cfg2<KIND>::PAIR_M;
+    if (gemm2_cluster4_enabled() && pair_tiles >= 2 && (pair_tiles % 2 == 0 || pair_tiles >= 24))
+        return gemm2_launch_cl<KIND, Epi, 4>(g, ep, stream);
+    return gemm2_launch_cl<KIND, Epi, 2>(g, ep, stream);
+}
+
+template <int KIND, class Epi, int CL>
+int gemm2_launch_cl(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t stream) {
     using C = Cfg2<KIND>;
+    constexpr int PAIRS = CL / 2;
     constexpr int ELEM = C::ELEM;
     const bool bf = KIND == 1;
     constexpr bool SW32 = KIND != 1;
@@ -299,7 +386,7 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     if (!g.a_mn) rc = make_tmap_2d(&tmA, g.A, bf, g.K, g.M, (uint64_t)g.lda * ELEM, C::BLOCK_K, BLOCK_M);
     else         rc = make_tmap_2d(&tmA, g.A, bf, g.M, g.K, (uint64_t)g.lda * ELEM, C::CHUNK, C::BLOCK_K, SW32);
     if (rc) return rc;
-    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, bf, g.K, g.N, (uint64_t)g.ldb * ELEM, C::BLOCK_K, C::HALF_N);
+    if (!g.b_mn) rc = make_tmap_2d(&tmB, g.B, bf, g.K, g.N, (uint64_t)g.ldb * ELEM, C::BLOCK_K, C::HALF_N / PAIRS);
     else         rc = make_tmap_2d(&tmB, g.B, bf, g.N, g.K, (uint64_t)g.ldb * ELEM, C::CHUNK, C::BLOCK_K, SW32);
     if (rc) return rc;
     const int out_elem = g.out_bf16 ? 2 : 4;
@@ -326,7 +413,7 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     TileSched p;
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.num_kb = (g.K + C::BLOCK_K - 1) / C::BLOCK_K;
-    p.m_tiles = (g.M + C::PAIR_M - 1) / C::PAIR_M;
+    p.m_tiles = (g.M + C::PAIR_M * PAIRS - 1) / (C::PAIR_M * PAIRS);
     p.n_tiles = (g.N + C::BLOCK_N - 1) / C::BLOCK_N;
     p.a_mn = g.a_mn; p.b_mn = g.b_mn;
     p.accumulate = g.accumulate;
@@ -334,7 +421,24 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     p.aux_tma = aux_tma ? 1 : 0;
     p.in_f16 = g.dtype == 3;
     p.out_f16 = g.out_f16;
-    const int pairs_max = num_sms() / 2;
+    auto kern = gemm2_kernel<KIND, Epi, CL>;
+    static int clusters_max = 0;              // per instantiation: co-resident clusters of this kernel on the device
+    if (clusters_max == 0) {
+        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(num_sms() / CL * CL, 1, 1);
+        qc.blockDim = dim3(gemm2_threads<Epi>(), 1, 1);
+        qc.dynamicSmemBytes = C::SMEM_BYTES;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa; qc.numAttrs = 1;
+        int n = 0;
+        MOREC_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &qc));
+        if (n > num_sms() / CL) n = num_sms() / CL;
+        clusters_max = n > 0 ? n : 1;
+    }
+    const int pairs_max = clusters_max;
     int splits = 1;
     if (g.accumulate && g.allow_split_k) {
         const int tiles = p.m_tiles * p.n_tiles;
@@ -347,14 +451,16 @@ int gemm2_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t
     p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int pairs = total < pairs_max ? total : pairs_max;
-    auto kern = gemm2_kernel<KIND, Epi>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
-    kern<<<2 * pairs, gemm2_threads<Epi>(), C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
-    MOREC_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * pairs, 1, 1);
+    cfg.blockDim = dim3(gemm2_threads<Epi>(), 1, 1);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la; cfg.numAttrs = 1;
+    MOREC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p, ep));
     return MOREC_OK;
 }
 

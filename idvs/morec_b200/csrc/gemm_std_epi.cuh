@@ -152,33 +152,16 @@ struct StdEpi {
         for (int off = 0; off < bytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
     }
 
-    template <bool FAST>
+    // One 32-column chunk of this thread's row: activation / gradient math on x, then staging + (grouped) TMA store.
+    template <bool FAST, bool O16, bool F16>
     __device__ __forceinline__ static void chunk(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
-                                                 EpiStore& st, const uint32_t (&v)[32], int c, int row, int row0,
-                                                 int n0, bool add_bias, const TileSched& s, const uint4 (&araw)[4],
-                                                 bool have_raw) {
+                                                 EpiStore& st, float (&x)[32], int c, int row, int row0, int n0,
+                                                 const TileSched& s, const uint4 (&araw)[4], bool have_raw) {
         const int col0 = n0 + c * 32;
-        const bool obf = s.out_bf16 != 0;
         constexpr int ns = kStreams;
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * ep.alpha;
-        if (add_bias) {
-            if (col0 + 32 <= s.N) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
-                    x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (col0 + j < s.N) x[j] += __ldg(ep.bias + col0 + j);
-            }
-        }
         if constexpr (MODE == MOREC_EPI_GELU) {
             // pre-activation to C2 first (kept for the backward), then the activation to C
-            st.put(&tmC2, x, c, obf, 1, 2);
+            st.template put_c<ns, O16, F16>(&tmC2, x, c, 1);
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = FAST ? gelu_fast(x[j]) : gelu_erf(x[j]);
         } else if constexpr (MODE == MOREC_EPI_GELU_DGELU) {
@@ -197,41 +180,46 @@ struct StdEpi {
                     x[j] = gelu_erf(x[j]);
                 }
             }
-            st.put(&tmC2, d, c, obf, 1, 2);
-        } else if constexpr (MODE == MOREC_EPI_MUL_AUX) {
-            float a[32];
-            if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
-            else load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] *= a[j];
+            st.template put_c<ns, O16, F16>(&tmC2, d, c, 1);
         } else if constexpr (MODE == MOREC_EPI_GELU_NOSAVE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = FAST ? gelu_fast(x[j]) : gelu_erf(x[j]);
         } else if constexpr (MODE == MOREC_EPI_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-        } else if constexpr (MODE == MOREC_EPI_MUL_GELU_GRAD) {
+        } else if constexpr (kAuxMode) {
             float a[32];
             if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
             else load_aux(ep, a, row, col0, s.M, s.N);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] *= FAST ? gelu_fast_grad(a[j]) : gelu_erf_grad(a[j]);
-        } else if constexpr (MODE == MOREC_EPI_MUL_RELU_GRAD) {
-            float a[32];
-            if (have_raw) { if (ep.aux_f16) aux_unpack<true>(araw, a); else aux_unpack<false>(araw, a); }
-            else load_aux(ep, a, row, col0, s.M, s.N);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = a[j] > 0.f ? x[j] : 0.f;
+            for (int j = 0; j < 32; ++j) {
+                if constexpr (MODE == MOREC_EPI_MUL_AUX) x[j] *= a[j];
+                else if constexpr (MODE == MOREC_EPI_MUL_GELU_GRAD) x[j] *= FAST ? gelu_fast_grad(a[j]) : gelu_erf_grad(a[j]);
+                else x[j] = a[j] > 0.f ? x[j] : 0.f;
+            }
         }
-        st.put(&tmC, x, c, obf, 0, ns);
-        st.end_chunk(c, n0, row0, obf, s.accumulate != 0, ns);
+        st.template put_c<ns, O16, F16>(&tmC, x, c, 0);
+        st.template end_chunk_c<ns, O16>(c, n0, row0, s.accumulate != 0);
     }
 
-    // KIND 2 (3xTF32, the parity mode) keeps erff; the fast modes use the polynomial erf (common.cuh)
+    // KIND 2 (3xTF32, the parity mode) keeps erff; the fast modes use the polynomial erf (common.cuh).
+    // Specialised on the output element type at the tile level (the flags are warp-uniform kernel parameters).
     template <int KIND, int BLOCK_N>
     __device__ __forceinline__ static void tile(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                                                 uint32_t taddr, EpiStore& st, int m0, int q, int n0, int split,
                                                 const TileSched& s, int cg, int ncg) {
+        if (s.out_bf16) {
+            if (st.f16) tile_t<KIND, BLOCK_N, true, true>(ep, tmC, tmC2, taddr, st, m0, q, n0, split, s, cg, ncg);
+            else tile_t<KIND, BLOCK_N, true, false>(ep, tmC, tmC2, taddr, st, m0, q, n0, split, s, cg, ncg);
+        } else {
+            tile_t<KIND, BLOCK_N, false, false>(ep, tmC, tmC2, taddr, st, m0, q, n0, split, s, cg, ncg);
+        }
+    }
+
+    template <int KIND, int BLOCK_N, bool O16, bool F16>
+    __device__ __forceinline__ static void tile_t(const Params& ep, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                                                  uint32_t taddr, EpiStore& st, int m0, int q, int n0, int split,
+                                                  const TileSched& s, int cg, int ncg) {
         constexpr bool FAST = KIND != 2;
         const int row0 = m0 + q * 32;
         if (row0 >= s.M) return;   // warp-uniform
@@ -240,9 +228,14 @@ struct StdEpi {
         chunk_range<BLOCK_N>(s, n0, cg, ncg, c_lo, c_end);
         if (c_lo >= c_end) return;
         st.c_end = c_end;
-        const bool add_bias = ep.bias != nullptr && split == 0;
-        // software pipeline: the TMEM load (and the packed bf16 side input) of chunk c+1 is in flight while chunk c is
-        // processed
+        // bias: lane j holds the bias of column j of the chunk (ONE load per lane and chunk, fetched a chunk ahead and
+        // broadcast by shuffle) -- the former 8 x LDG.128 per thread and chunk sat on the critical path of every chunk
+        // (ncu: 10 % of the GELU epilogue's samples were long-scoreboard stalls on the first bias add)
+        const float* bias = (ep.bias != nullptr && split == 0) ? ep.bias : nullptr;
+        auto bias_of = [&](int c) -> float {
+            const int col = n0 + c * 32 + st.lane;
+            return (bias != nullptr && col < s.N) ? __ldg(bias + col) : 0.f;
+        };
         const bool tma_aux = st.aux_groups > 0;
         if (tma_aux) {                                  // side input staged by pre_tile(): wait for it to land
             mbar_wait(st.aux_bar, st.aux_phase);
@@ -253,26 +246,29 @@ struct StdEpi {
         uint4 ra[4], rb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) ra[j] = rb[j] = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t va[32], vb[32];
+        uint32_t v[32];
         if (direct) load_aux_raw(ep, ra, row, n0 + c_lo * 32, s.M);
-        tmem_ld32(taddr + c_lo * 32, va);
+        tmem_ld32(taddr + c_lo * 32, v);
+        float b_next = bias_of(c_lo);
+        // software pipeline with ONE copy of the chunk code: the accumulator registers are consumed (scaled, biased)
+        // first, then the TMEM load of chunk c+1 is issued into the same registers and is in flight during the math
 #pragma unroll 1
-        for (int c = c_lo; c < c_end; c += 2) {
+        for (int c = c_lo; c < c_end; ++c) {
             tc_wait_ld();
+            const float bc = b_next;
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(v[j]), ep.alpha, __shfl_sync(0xffffffffu, bc, j));
             if (c + 1 < c_end) {
-                tmem_ld32(taddr + (c + 1) * 32, vb);
+                tmem_ld32(taddr + (c + 1) * 32, v);
+                b_next = bias_of(c + 1);
                 if (direct) load_aux_raw(ep, rb, row, n0 + (c + 1) * 32, s.M);
             }
             if (tma_aux) load_aux_smem(st, ra, c);
-            chunk<FAST>(ep, tmC, tmC2, st, va, c, row, row0, n0, add_bias, s, ra, raw);
-            if (c + 1 < c_end) {
-                tc_wait_ld();
-                if (c + 2 < c_end) {
-                    tmem_ld32(taddr + (c + 2) * 32, va);
-                    if (direct) load_aux_raw(ep, ra, row, n0 + (c + 2) * 32, s.M);
-                }
-                if (tma_aux) load_aux_smem(st, rb, c + 1);
-                chunk<FAST>(ep, tmC, tmC2, st, vb, c + 1, row, row0, n0, add_bias, s, rb, raw);
+            chunk<FAST, O16, F16>(ep, tmC, tmC2, st, x, c, row, row0, n0, s, ra, raw);
+            if (direct) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ra[j] = rb[j];
             }
         }
     }

@@ -185,6 +185,63 @@ struct EpiStore {
         }
         ++grp;
     }
+    // Compile-time flavour of put()/end_chunk() for the standard epilogues (two sub-buffers per warp in both kernels):
+    // NS output streams, O16 = 16-bit outputs (F16: IEEE half).  One sub-buffer per stream and group, a group is one
+    // chunk (fp32) or two (16-bit); NS == 1 ping-pongs between the two sub-buffers.  All index arithmetic folds to
+    // shifts and masks: the runtime form above spent ~15 % of the GELU epilogue in integer division and control code.
+    template <int NS, bool O16, bool F16>
+    __device__ __forceinline__ void put_c(const CUtensorMap* tmap, const float (&x)[32], int c, int stream) {
+        constexpr int CPS = O16 ? 2 : 1;
+        constexpr bool PINGPONG = NS == 1;
+        const int g = c & (CPS - 1);
+        if (g == 0 && stream == NS - 1) {
+            if (lane == 0) {
+                if (PINGPONG) tma_store_wait_read<1>();
+                else tma_store_wait_read<0>();
+            }
+            __syncwarp();
+        }
+        tm[stream] = tmap;
+        const int half = PINGPONG ? (grp & 1) : 0;
+        uint8_t* rowp = bufs + (half * NS + stream) * kEpiBufBytes + lane * 128;
+        if constexpr (!O16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int pj = j ^ (lane & 7);
+                *reinterpret_cast<float4*>(rowp + pj * 16) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pj = (g * 4 + j) ^ (lane & 7);
+                uint4 u;
+                u.x = pack2_16(x[8 * j], x[8 * j + 1], F16); u.y = pack2_16(x[8 * j + 2], x[8 * j + 3], F16);
+                u.z = pack2_16(x[8 * j + 4], x[8 * j + 5], F16); u.w = pack2_16(x[8 * j + 6], x[8 * j + 7], F16);
+                *reinterpret_cast<uint4*>(rowp + pj * 16) = u;
+            }
+        }
+    }
+    template <int NS, bool O16>
+    __device__ __forceinline__ void end_chunk_c(int c, int n0, int row0, bool reduce_add) {
+        constexpr int CPS = O16 ? 2 : 1;
+        constexpr bool PINGPONG = NS == 1;
+        const int g = c & (CPS - 1);
+        if (g != CPS - 1 && c != c_end - 1) return;
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int half = PINGPONG ? (grp & 1) : 0;
+        if (lane == 0) {
+            const int col_base = n0 + (c - g) * 32;
+#pragma unroll
+            for (int st = 0; st < NS; ++st) {
+                const uint32_t src = smem_u32(bufs + (half * NS + st) * kEpiBufBytes);
+                if (reduce_add) tma_reduce_add_2d(tm[st], src, col_base, row0);
+                else tma_store_2d(tm[st], src, col_base, row0);
+            }
+            tma_store_commit();
+        }
+        ++grp;
+    }
     // compatibility helper used by single-stream epilogues
     __device__ __forceinline__ void emit(const CUtensorMap* tmap, const float (&x)[32], int c, int n0, int row0,
                                          bool out_bf16, bool reduce_add, int slot = 0, int nslots = 1) {

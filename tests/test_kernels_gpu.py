@@ -25,7 +25,8 @@ def rel(a, b):
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
 def test_gemm_layouts(lib, dt, x3, tol, a_mn, b_mn):
     with lib.fp32_mode(x3):
-        for (M, N, K) in [(128, 128, 32), (392, 200, 104), (1600, 512, 512), (2048, 768, 3072)]:
+        # (6296, 512, 192): 25 CTA-pair row tiles -> 13 four-CTA clusters, the last one with a pair entirely past M
+        for (M, N, K) in [(128, 128, 32), (392, 200, 104), (1600, 512, 512), (2048, 768, 3072), (6296, 512, 192)]:
             torch.manual_seed(M + N + K)
             A = torch.randn((K, M) if a_mn else (M, K), device="cuda").to(dt)
             B = torch.randn((K, N) if b_mn else (N, K), device="cuda").to(dt)

@@ -7,7 +7,7 @@ from idvs.morec_b200 import lib
 M, N, K = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 mode = sys.argv[4] if len(sys.argv) > 4 else "tf32"
 layout = sys.argv[5] if len(sys.argv) > 5 else "kk"
-dt = torch.bfloat16 if mode == "bf16" else torch.float32
+dt = torch.bfloat16 if mode == "bf16" else torch.float16 if mode == "fp16" else torch.float32
 a_mn, b_mn = {"kk": (False, False), "kmn": (False, True), "mnmn": (True, True)}[layout]
 A = torch.randn((K, M) if a_mn else (M, K), device="cuda").to(dt)
 B = torch.randn((K, N) if b_mn else (N, K), device="cuda").to(dt)
