@@ -12,8 +12,11 @@ Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with the W+K bat
 `e2e` = the same through the public Model API with host buffers (pinned H2D of each step's batch and a D2H read of
 the loss inside the timed region); `roofline` = the dominant kernel (the tcgen05 GEMM) timed with CUDA events on the
 launching stream inside the timed region; `cpu_baseline` = the oracle port on the host cores on a bounded sample.
-`--impl reference` times the CPU oracle port instead (the reference is Python and cannot travel to the GPU box;
-oracle/morec_oracle.py restates it and is pinned to goldens generated from the unmodified reference).
+`--impl reference` times the UNMODIFIED reference Model (baseline/_ref, mirrored by __graft_entry__.build()) on the
+host cores at the full batch; without that copy, the oracle port on a bounded sample (`cpu_baseline.kind`).
+Extra keys: `roofline_scoring` (K8, the fused scoring + CE kernel, at the cfg-3 and the 8-GPU all-gathered shapes,
+against both rooflines), `flops_dense_vs_executed` (tensor work actually executed vs the reference's dense count),
+`modes` (seq/s of every precision mode), `roofline.traffic` (ncu DRAM bytes of the dominant kernel, per launch).
 """
 import argparse
 import json
@@ -41,6 +44,15 @@ SWIN_T = dict(image_size=224, patch_size=4, num_channels=3, embed_dim=96, depths
               drop_path_rate=0.1, hidden_act="gelu", layer_norm_eps=1e-5)
 CFG_VISION = dict(B=32, L=10, T=0, D=512, heads=2, blocks=2, N=50000, drop=0.1,
                   lr=1e-4, fine_tune_lr=1e-4, l2=0.1, fine_tune_l2=0.1)    # train_swin_tiny.py
+
+
+# DRAM traffic of the dominant kernel from one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum
+# of ONE launch); a tensor-bound kernel: the figure only shows that nothing is re-read (algorithmic = A + B + C once)
+TRAFFIC = {"bytes": 110831360, "algorithmic_bytes": 23207424 + 2 * 73955328,
+           "launch": "gemm2_kernel<f16, GELU+GELU' epilogue> 12037 x 3072 x 768 (FFN1 forward: A 18.5 MB + B 4.7 MB read, two "
+                     "12037 x 3072 fp16 outputs written; 87.5 MB of the 147.9 MB written had left L2 when the kernel ended)",
+           "other": "plain 12037 x 768 x 768: 19.72 MB read = A + B exactly, 0 written back inside the kernel",
+           "source": "profiles/r02_ncu_gemm_epilogues.txt"}
 
 
 def make_args(cfg):
@@ -411,6 +423,80 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     return step, host, resident, h2d_bytes
 
 
+
+# ------------------------------------------------------------------------------------------------ K8 roofline
+def scoring_roofline(cfg, peaks, dev):
+    """K8 = fused scoring + debias + masks + CE (model/model.py:45-67).  Forward = mask pre-pass + scoring GEMM with the
+    CE-partials epilogue + combine; backward = dlogits GEMM + dP and dE GEMMs.  Timed alone (CUDA events, operands
+    L2-warm as in the step, where E has just been written) at the single-GPU shape and at the 8-GPU all-gathered
+    shape, in the arithmetic the step uses for it (3xTF32 on fp32 operands) and in fp16.  Algorithmic bytes per
+    SURVEY.md 8(d): s*(R+C)*D + 12*C + 12*R forward (the [R,C] logits are never counted), the same plus the dP / dE
+    outputs backward; FLOPs 2*R*C*D forward, 6*R*C*D backward."""
+    import torch
+    from idvs.morec_b200 import lib
+    from idvs.morec_b200.synth import synth_batch
+    B, L, D = cfg["B"], cfg["L"], cfg["D"]
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tens = float(peaks.get("bf16_tflops", 1604.0))
+    out = []
+    for G in (1, 8):
+        bs = [synth_batch(B, L, cfg["N"], 0, seed=100 + g, modal=False, n_users_pop=2000) for g in range(G)]
+        ids_all = torch.cat([b["ids"].reshape(-1) for b in bs]).to(dev)
+        ids_loc = bs[0]["ids"].to(dev)
+        lm = bs[0]["log_mask"].reshape(-1).to(dev)
+        R, C = B * L, ids_all.numel()
+        logp = torch.rand(C, device=dev).log()
+        g1 = torch.ones(1, device=dev)
+        for dt, x3, name, es in ((torch.float32, True, "fp32 (3xTF32, as in the step)", 4), (torch.float16, False, "fp16", 2)):
+            P = (torch.randn(R, D, device=dev) * 0.3).to(dt)
+            E = (torch.randn(C, D, device=dev) * 0.3).to(dt)
+
+            def fwd():
+                member, pad = lib.inbatch_mask(ids_loc, ids_all, B, L)
+                return (member, pad) + tuple(lib.inbatch_ce_fwd(P, E, member, pad, logp, lm, B, L))
+
+            def bwd(st):
+                member, pad, loss, row_lse, row_loss, sum_cnt = st[:6]
+                dS = lib.inbatch_ce_dlogits(P, E, member, pad, logp, lm, row_lse, g1, sum_cnt[1:2].contiguous(), B, L)
+                dP = torch.empty(R, D, device=dev, dtype=dt)
+                dE = torch.empty(C, D, device=dev, dtype=dt)
+                lib.gemm(dS, E, dP, M=R, N=D, K=C, lda=dS.stride(0), ldb=E.stride(0), ldc=D, a_mn=False, b_mn=True)
+                lib.gemm(dS, P, dE, M=C, N=D, K=R, lda=dS.stride(0), ldb=P.stride(0), ldc=D, a_mn=True, b_mn=True)
+
+            with lib.fp32_mode(x3):
+                st = fwd()
+                bwd(st)
+                torch.cuda.synchronize()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                n = 20
+                e0.record()
+                for _ in range(n):
+                    st = fwd()
+                e1.record()
+                for _ in range(n):
+                    bwd(st)
+                e2.record()
+                torch.cuda.synchronize()
+            us_f, us_b = e0.elapsed_time(e1) / n * 1e3, e1.elapsed_time(e2) / n * 1e3
+            by_f = es * (R + C) * D + 12 * C + 12 * R
+            by_b = by_f + es * (R + C) * D
+            fl_f, fl_b = 2.0 * R * C * D, 6.0 * R * C * D
+            tpk = tens * (1.0 / 6.0 if x3 else 1.0)       # 3 passes at the half-rate tf32 kind
+            out.append({"shape": f"R={R} C={C} D={D} (G={G})", "arith": name,
+                        "fwd_us": round(us_f, 1), "bwd_us": round(us_b, 1), "launches": {"fwd": 3, "bwd": 3},
+                        "alg_bytes_fwd": by_f, "fwd_gbs": round(by_f / us_f / 1e3, 1),
+                        "fwd_frac_hbm": round(by_f / us_f / 1e3 / hbm, 4),
+                        "fwd_tflops": round(fl_f / us_f / 1e6, 1), "fwd_frac_tensor": round(fl_f / us_f / 1e6 / tpk, 3),
+                        "bwd_tflops": round(fl_b / us_b / 1e6, 1), "bwd_frac_tensor": round(fl_b / us_b / 1e6 / tpk, 3),
+                        "hbm_floor_us": round(by_f / hbm / 1e3, 2), "tensor_floor_us": round(fl_f / tpk / 1e6, 2)})
+    return {"kernel": "K8: morec::inbatch_mask_kernel + gemm_kernel<.,CeFwdEpi> + inbatch_ce_combine_kernel (fwd); "
+                      "gemm_kernel<.,CeBwdEpi> + 2 x gemm (bwd)",
+            "peaks": {"hbm_gbs": hbm, "tensor_tflops_f16": tens, "tensor_tflops_3xtf32": round(tens / 6.0, 1)},
+            "shapes": out,
+            "note": "bound is the tensor roofline, not HBM: the algorithmic traffic is 3-30 MB for 2.7-22 GFLOP, so 60 % of "
+                    "the HBM peak would need > 3 PFLOP/s; *_frac_tensor is against the rate the arithmetic allows "
+                    "(3xTF32 = 1/6 of the f16 peak); at the G=1 shape the three launches sit on the launch-latency floor"}
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -426,6 +512,7 @@ def main():
     ap.add_argument("--workload", default="text", choices=["text", "vision"],
                     help="text = SASRec+BERT-base (headline, configs[2]); vision = SASRec+Swin-T (configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true", help="skip the K8 (scoring + CE kernel) roofline block")
     ap.add_argument("--d2h-plan", action="store_true", help="plan each step from a device->host copy of the ids and token "
                     "counts (one host wait per step) instead of from the ids the host already has")
     ap.add_argument("--cpu-sample-users", type=int, default=4)
@@ -492,7 +579,24 @@ def main():
     else:       # packed token count of a step = tokens of the batch's DISTINCT items
         import numpy as np
         lens = step.model._item_lens
-        big = max(range(len(host)), key=lambda i: int(lens[np.unique(host[i][0].numpy())].sum()))
+        if world > 1 and args.parallel == "global":
+            # a rank encodes its SHARE of the global batch's distinct items: regenerate every rank's ids (the synthetic
+            # generator is seeded per rank and batch) and take the batch whose largest share has the most tokens --
+            # the same batch index on every rank, the collectives of a step pair up by position
+            from idvs.morec_b200.parallel import plan_global_batch
+            from idvs.morec_b200.synth import synth_batch
+
+            def share_tokens(i):
+                ids_all = np.concatenate([synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * r + i,
+                                                      modal=False)["ids"].numpy().reshape(-1) for r in range(world)])
+                worst = 0
+                for r in range(world):
+                    pl = plan_global_batch(ids_all, world, r)
+                    worst = max(worst, int(lens[ids_all[pl.my_first_slots]].sum()))
+                return worst
+            big = max(range(len(host)), key=share_tokens)
+        else:
+            big = max(range(len(host)), key=lambda i: int(lens[np.unique(host[i][0].numpy())].sum()))
     step(*resident[big])
     for i in range(W - 1):
         step(*resident[i])
@@ -602,12 +706,32 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "morec::gemm2_kernel / gemm_kernel (tcgen05 CTA-pair and single-CTA GEMMs: every fwd / dgrad / wgrad / scoring launch)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": TRAFFIC["bytes"],
+                "traffic_detail": TRAFFIC,
                 "peak_source": peak_src, "launches_timed": gemm_n, "gemm_ms_per_step": gemm_ms / K,
                 "note": {"fp32": "3xTF32 parity mode: 3 tensor-core passes per algorithmic FLOP and kind::tf32 runs at half "
                                  "the bf16 rate, so the attainable fraction of the bf16 peak is 1/6",
                          "tf32": "kind::tf32 runs at half the bf16 rate: attainable fraction of the bf16 peak is 1/2",
                          "bf16": "kind::f16 on bf16 operands", "fp16": "kind::f16 on fp16 operands"}[args.mode]}
+    # tensor work executed vs the reference's dense count (it encodes all C slots x T tokens, pads and duplicates included)
+    flops_dv = None
+    scoring = None
+    if not vision:
+        import numpy as np
+        lens = step.model._item_lens
+        tok_exec = float(np.mean([int(lens[np.unique(host[W + i][0].numpy())].sum()) for i in range(K)]))
+        Hh, Ii, nl = BERT_BASE["hidden_size"], BERT_BASE["intermediate_size"], BERT_BASE["num_hidden_layers"]
+        per_tok = nl * 2.0 * (4 * Hh * Hh + 2 * Hh * Ii)           # forward GEMM FLOPs of one token through the tower
+        tok_dense = cfg["B"] * (cfg["L"] + 1) * cfg["T"]
+        executed = gemm_flops / K
+        dense = executed + 3.0 * per_tok * (tok_dense - tok_exec)
+        flops_dv = {"executed_tflop_per_step": executed / 1e12, "reference_dense_tflop_per_step": dense / 1e12,
+                    "executed_over_dense": executed / dense, "tokens_executed_per_step": tok_exec,
+                    "tokens_dense_per_step": tok_dense,
+                    "note": "pad word pieces, pad item slots and duplicate items are not encoded (bit-identical loss with "
+                            "dropout off, tests/test_parity_gpu.py); the roofline counts executed FLOPs only"}
+        if not args.no_scoring:
+            scoring = scoring_roofline(cfg, peaks, dev)
     cpu_base = None
     if not args.no_cpu_baseline and not vision:
         if ref_root() is not None and not args.cpu_port:
@@ -628,7 +752,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "sequences/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "host_issue_ms_per_step": 1e3 * t_issue / K, "host_ms_each_step": step_host_ms,
             "loss_first_last_e2e": [e2e_losses[0], e2e_losses[-1]] if e2e_losses else None,
-            "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline, "modes": modes,
+            "allocator_events_in_timed_region": alloc_delta, "clocks": clocks, "roofline": roofline,
+            "roofline_scoring": scoring, "flops_dense_vs_executed": flops_dv, "modes": modes,
             "cpu_baseline": cpu_base}
     print(json.dumps(line))
     if world > 1:

@@ -48,6 +48,90 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t
         "r"(rank)
         : "memory");
 }
+// ---- dynamic tile scheduling: cluster-scope release / acquire hand-over of the next work item
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(local_bar),
+        "r"(rank)
+        : "memory");
+}
+// consumer -> scheduler "slot read": RELAXED.  A release arrive by the MMA-issuing thread waited for its outstanding
+// tensor-core work (measured: ~2,000 idle cycles at every tile boundary); nothing has to be published here -- the
+// consumer only read the slot, and the arrive's address depends on the value read, so it cannot overtake the load.
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t local_bar, uint32_t rank, uint32_t dep) {
+    asm volatile(
+        "{\n\t.reg .b32 ra, rz;\n\t"
+        "and.b32 rz, %2, 0;\n\t"
+        "add.u32 rz, rz, %0;\n\t"
+        "mapa.shared::cluster.u32 ra, rz, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(local_bar),
+        "r"(rank), "r"(dep)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni WAITC_DONE;\n\t"
+        "bra.uni WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t local_addr, uint32_t rank, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(local_addr),
+        "r"(rank), "r"(v)
+        : "memory");
+}
+// Work items are dealt DYNAMICALLY (CL == 2): the first item of a pair is its index, every further one comes from a
+// global counter.  A scheduler thread (leader CTA, warp 3) draws item i+1 as soon as the producer has STARTED item i
+// and publishes it through a 4-deep ring in the shared memory of BOTH CTAs:
+//   pstart    (leader's, count 1)           the leader's producer arrives when it starts an item (look-ahead of one item:
+//                                           a pair never hoards work it has not begun while other pairs run dry)
+//   sfull[s]  (per CTA, count 1)            the scheduler arrives (release.cluster) after writing slot s in both CTAs
+//   sempty[s] (leader's, count 3 + 8*groups) every consumer -- both producers, the MMA warp, all epilogue warps of both
+//                                           CTAs -- arrives after reading slot s
+// The hand-over must not run on the producer thread: its two cluster-scope release arrives cost ~2,000 cycles, more
+// than the ~1,700 cycles by which the operand ring (6 stages, ~2,900 cycles TMA latency under load) is ahead of the
+// tensor core -- measured 51.4 -> 56.9 us at 12037 x 3072 x 768 with the producer as scheduler.
+// A pair whose CTAs became resident late (the SMs were held by an NCCL kernel or by a GEMM of the other stream) simply
+// takes fewer items; with the static `w += n_pairs` deal such a pair ran its whole share after everybody else had
+// finished (measured: GEMM time per step 7.10 -> 7.75 ms with the gradient all-reduce of a 2-GPU run alongside).
+constexpr int kSchedRing = 4;
+struct SchedRing {
+    uint32_t sfull, sempty, tiles;      // shared-memory addresses (this CTA)
+    uint32_t lead_rank;
+    // consumer side: work item number `it` (>= 1) of this pair.  WARP: called by all 32 lanes of a converged warp (one
+    // arrival per warp, after every lane has read the slot); otherwise by a single thread
+    template <bool WARP>
+    __device__ __forceinline__ int next(int it, int lane) const {
+        const int slot = it & (kSchedRing - 1);
+        const uint32_t ph = ((uint32_t)(it - 1) / kSchedRing) & 1u;
+        mbar_wait_acquire_cluster(sfull + slot * 8, ph);
+        int w;
+        asm volatile("ld.shared::cta.u32 %0, [%1];" : "=r"(w) : "r"(tiles + slot * 4) : "memory");
+        if (WARP) __syncwarp();
+        if (!WARP || lane == 0) mbar_arrive_relaxed_cluster(sempty + slot * 8, lead_rank, (uint32_t)w);
+        return w;
+    }
+    // leader producer thread: hand item `w` (number `it`) to every consumer of the pair
+    __device__ __forceinline__ void publish(int it, int w) const {
+        const int slot = it & (kSchedRing - 1);
+        const uint32_t ph = ((uint32_t)(it - 1) / kSchedRing) & 1u;
+        mbar_wait_acquire_cluster(sempty + slot * 8, ph ^ 1u);
+        st_shared_cluster_u32(tiles + slot * 4, lead_rank, (uint32_t)w);
+        st_shared_cluster_u32(tiles + slot * 4, lead_rank + 1, (uint32_t)w);
+        mbar_arrive_release_cluster(sfull + slot * 8, lead_rank);
+        mbar_arrive_release_cluster(sfull + slot * 8, lead_rank + 1);
+    }
+};
+
 __device__ __forceinline__ void tma_load_2d_2sm(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1) {
     // executed by both CTAs; the peer bit of the barrier address is cleared so the bytes are credited to CTA 0
     asm volatile(
@@ -142,6 +226,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
     uint64_t* aux_bars = bars + 32;               // [8] one per epilogue warp: side-input TMA loads
+    uint64_t* sfull_bar = bars + 40;              // [kSchedRing] dynamic scheduling (see SchedRing)
+    uint64_t* sempty_bar = bars + 44;             // [kSchedRing]
+    uint32_t* sched_tiles = reinterpret_cast<uint32_t*>(bars + 48);   // [kSchedRing]
+    uint64_t* pstart_bar = bars + 52;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -168,6 +256,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(smem_u32(&tempty_bar[s]), 2 * kEpiWarps * Epi::kGroups);
         }
         for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&aux_bars[s]), 1);
+        for (int s = 0; s < kSchedRing; ++s) {
+            mbar_init(smem_u32(&sfull_bar[s]), 1);
+            mbar_init(smem_u32(&sempty_bar[s]), 3 + 2 * kEpiWarps * Epi::kGroups);
+        }
+        mbar_init(smem_u32(pstart_bar), 1);
         mbar_fence_init();
     }
     cluster_sync_all();                       // barrier inits of both CTAs visible before any remote arrive / TMA
@@ -183,6 +276,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int pair = blockIdx.x / CL;             // work is dealt to clusters; the pairs of a cluster share (n-tile, split)
     const int n_pairs = gridDim.x / CL;
     const int total_work = p.m_tiles * p.n_tiles * p.splits;      // m_tiles counts (PAIRS x 256)-row cluster tiles here
+    const bool dyn = CL == 2 && p.sched_ctr != nullptr;
+    SchedRing ring;
+    ring.sfull = smem_u32(sfull_bar); ring.sempty = smem_u32(sempty_bar); ring.tiles = smem_u32(sched_tiles);
+    ring.lead_rank = lead_rank;
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
@@ -190,7 +287,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             [[maybe_unused]] int tr = 0;
-            for (int w = pair; w < total_work; w += n_pairs) {
+            int it = 0;
+            for (int w = pair; w < total_work;) {
+                if (dyn && leader) mbar_arrive(smem_u32(pstart_bar));         // the scheduler may draw the next item
                 const int split = w % p.splits;
                 const int tile = w / p.splits;
                 const int m0 = ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M;
@@ -244,6 +343,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                ++it;
+                w = dyn ? ring.template next<false>(it, 0) : w + n_pairs;
+            }
+        }
+    } else if (warp == 3 && leader && dyn) {
+        // ================================ work-item scheduler (leader CTA only) ================================
+        if (lane == 0) {
+            int w = pair;
+            for (int it = 0; w < total_work;) {
+                mbar_wait(smem_u32(pstart_bar), (uint32_t)it & 1u);           // the producer has started item `it`
+                w = n_pairs + atomicAdd(p.sched_ctr, 1);
+                ++it;
+                ring.publish(it, w);
+            }
+            // this pair has drawn its last item; the last pair of the grid to get here re-arms the counter slot
+            if (atomicAdd(p.sched_ctr + 1, 1) == n_pairs - 1) {
+                p.sched_ctr[0] = 0;
+                p.sched_ctr[1] = 0;
+                __threadfence();
             }
         }
     } else if (warp == 1 && leader) {
@@ -257,7 +375,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int acc = 0;
         uint32_t acc_phase = 0;
         [[maybe_unused]] int tr = 0, trt = 0;
-        for (int w = pair; w < total_work; w += n_pairs) {
+        int it = 0;
+        for (int w = pair; w < total_work;) {
             const int split = w % p.splits;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
@@ -292,6 +411,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ++it;
+            w = dyn ? ring.template next<true>(it, lane) : w + n_pairs;
         }
     } else if (warp >= 4 && warp < 4 + 4 * Epi::kGroups) {
         // ================================ epilogue (both CTAs, own 128 rows) ================================
@@ -314,12 +435,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             Epi::template prefetch<C::BLOCK_N>(ep, ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
                                                (tile % p.n_tiles) * C::BLOCK_N, p);
         }
-        for (int w = pair; w < total_work; w += n_pairs) {
+        int it = 0;
+        for (int w = pair; w < total_work;) {
             const int split = w % p.splits;
             const int tile = w / p.splits;
             const int m0 = ((tile / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * C::BLOCK_N;
-            if (w + n_pairs < total_work) {                 // ... and of the next tile, one tile time ahead
+            if (!dyn && w + n_pairs < total_work) {         // ... and of the next tile, one tile time ahead (static deal only)
                 const int nt = (w + n_pairs) / p.splits;
                 Epi::template prefetch<C::BLOCK_N>(ep, ((nt / p.n_tiles) * PAIRS + (int)psub) * C::PAIR_M + (int)rank * BLOCK_M + q * 32 + lane,
                                                    (nt % p.n_tiles) * C::BLOCK_N, p);
@@ -336,6 +458,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (warp == 4 && lane == 0) MOREC_TRACE(5, trt);
             ++trt;
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            ++it;
+            w = dyn ? ring.template next<true>(it, lane) : w + n_pairs;
         }
         if (lane == 0) tma_store_wait<0>();
         __syncwarp();
@@ -411,6 +535,7 @@ int gemm2_launch_cl(const GemmArgs& g, const typename Epi::Params& ep, cudaStrea
         tmC2 = tmC;
     }
     TileSched p;
+    p.sched_ctr = CL == 2 ? gemm_sched_slot() : nullptr;
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.num_kb = (g.K + C::BLOCK_K - 1) / C::BLOCK_K;
     p.m_tiles = (g.M + C::PAIR_M * PAIRS - 1) / (C::PAIR_M * PAIRS);

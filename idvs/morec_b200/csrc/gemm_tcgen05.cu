@@ -2,6 +2,9 @@
 // gemm_std_m<MODE>.cu, one translation unit per epilogue mode.
 #include "gemm_std_epi.cuh"
 
+#include <stdlib.h>
+
+#include <atomic>
 #include <mutex>
 
 namespace morec {
@@ -52,6 +55,31 @@ int make_tmap_2d(CUtensorMap* map, const void* base, bool is_bf16, uint64_t inne
         return MOREC_ERR_CUDA;
     }
     return MOREC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dynamic tile scheduling of the CTA-pair kernel: counter pool
+// ------------------------------------------------------------------------------------------------
+constexpr int kSchedSlots = 512;
+__device__ int g_sched_ctr[kSchedSlots * 2];          // zero-initialised; every kernel leaves its slot zeroed again
+
+int* gemm_sched_slot() {
+    // OPT-IN (MOREC_GEMM_DYN=1).  Measured on B200: free when a GEMM runs alone (12037x3072x768: 51.4 us either way),
+    // but no gain where it was expected to help -- with the 2-GPU gradient all-reduce alongside, GEMM time per step
+    // stayed at 7.76 ms (static: 7.75; 7.1-7.2 on one GPU), and the single-GPU step went 10.74 -> 10.86 ms.  The
+    // slowdown under NCCL is therefore not late-starting CTA pairs.
+    static const bool enabled = []() { const char* e = getenv("MOREC_GEMM_DYN"); return e && e[0] == '1'; }();
+    if (!enabled) return nullptr;
+    static int* base[16] = {nullptr};
+    static std::atomic<unsigned> seq{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!base[dev]) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_sched_ctr) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        base[dev] = static_cast<int*>(ptr);
+    }
+    return base[dev] + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
 }
 
 }  // namespace morec

@@ -58,7 +58,13 @@ struct TileSched {
     int aux_tma;           // 1: tmC2 describes the epilogue side input (16-bit) and the CTA-pair kernel stages it by TMA
     int in_f16;            // KIND 1 operands are IEEE half (instruction-descriptor format 0) instead of bfloat16 (1)
     int out_f16;           // 16-bit outputs are IEEE half
+    int* sched_ctr;        // CTA-pair kernel, dynamic tile scheduling: {next work item, finished pairs} (null: static)
 };
+
+// One {work counter, finished-pairs counter} slot per launch of the CTA-pair kernel (round-robin over a small pool;
+// the last pair to finish zeroes its slot).  Returns a device pointer to two ints, or null when dynamic scheduling
+// is disabled (MOREC_GEMM_DYN=0).
+int* gemm_sched_slot();
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type = 2 /* SWIZZLE_128B */) {
@@ -519,6 +525,7 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
     }
 
     TileSched p;
+    p.sched_ctr = nullptr;
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.num_kb = (g.K + C::BLOCK_K - 1) / C::BLOCK_K;
     p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;

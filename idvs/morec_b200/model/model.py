@@ -169,7 +169,7 @@ class Model(torch.nn.Module):
         the step is planned without any device->host synchronisation."""
         if self.parallel_mode == "global" and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
-            return self._forward_global(sample_items_id, sample_items, log_mask, local_rank)
+            return self._forward_global(sample_items_id, sample_items, log_mask, local_rank, host_ids)
         dev = sample_items_id.device
         if self._log_pop is None or self._log_pop.device != dev:
             self.pop_prob_list = self.pop_prob_list.to(dev)
@@ -197,9 +197,19 @@ class Model(torch.nn.Module):
         return loss
 
     # -------------------------------------------------------------------------------------------
-    def _forward_global(self, sample_items_id, sample_items, log_mask, local_rank):
+    def _host_group(self):
+        """CPU (gloo) process group for the host-side exchange of the batch's item ids in `global` mode: created once,
+        collectively (every rank reaches its first host-planned global step together)"""
+        import torch.distributed as dist
+        if getattr(self, "_gloo_group", None) is None:
+            self._gloo_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+        return self._gloo_group
+
+    def _forward_global(self, sample_items_id, sample_items, log_mask, local_rank, host_ids=None):
         """`global` multi-GPU mode: see idvs/morec_b200/parallel.py.  Equals the reference at batch G*B in one
-        process: every item of the global batch is encoded once, one all-gather of embeddings."""
+        process: every item of the global batch is encoded once, one all-gather of embeddings.
+        With `host_ids` (+ set_item_content) the global plan is made from a HOST all-gather of the ids (gloo, 13 KB
+        per rank) and the catalogue's static token counts: no device->host wait, the host runs ahead of the GPU."""
         import torch.distributed as dist
         from .. import parallel as par
         dev = sample_items_id.device
@@ -223,22 +233,40 @@ class Model(torch.nn.Module):
             single = len(te.newsname) == 1 and te.attributes2start[te.newsname[0]] == 0
             if single and items_all.dtype != torch.int64:
                 items_all = items_all.to(torch.int64)
-            # ONE host wait: ids + per-slot token counts; the weight casts are issued behind the copies
-            h = lib.d2h_begin([ids_all, lib.mask_row_lens(items_all, T)] if single else [ids_all])
-            prep = te.text_encoders['title'].prepare() if single else None
-            got = lib.d2h_end(h)
-            plan = par.plan_global_batch(got[0], G, rank)                         # host index arithmetic
+            hp = self._host_plan_inputs(ids_flat, host_ids, C) if single else None
+            if hp is not None:
+                # host-side plan: ids travel between the hosts, token counts come from the catalogue
+                mine_t = torch.from_numpy(np.ascontiguousarray(hp[0]))
+                parts = [torch.empty_like(mine_t) for _ in range(G)]
+                dist.all_gather(parts, mine_t, group=self._host_group())
+                ids_all_np = torch.cat(parts).numpy()
+                lens_all = self._item_lens[ids_all_np]
+                prep = te.text_encoders['title'].prepare()
+            else:
+                # ONE host wait: ids + per-slot token counts; the weight casts are issued behind the copies
+                h = lib.d2h_begin([ids_all, lib.mask_row_lens(items_all, T)] if single else [ids_all])
+                prep = te.text_encoders['title'].prepare() if single else None
+                got = lib.d2h_end(h)
+                ids_all_np, lens_all = got[0], (got[1] if single else None)
+            plan = par.plan_global_batch(ids_all_np, G, rank)                     # host index arithmetic
             n_mine = int(plan.my_first_slots.size)
-            my_items = items_all[lib.h2d(plan.my_first_slots, dev)]
-            if n_mine > 0:
-                E_mine = te(my_items, got[1][plan.my_first_slots] if single else None, prep)
-            else:
-                E_mine = torch.zeros(0, D, device=dev, dtype=adt)
-            pad_idx = np.full(plan.u_max, -1, dtype=np.int32)
-            pad_idx[:n_mine] = np.arange(n_mine, dtype=np.int32)
-            if n_mine > 0:
+            enc_slots = plan.my_first_slots
+            if n_mine == 0:
+                # this rank owns no distinct item of the global batch (n_unique < G, e.g. the short last batch of an
+                # epoch): it still runs the tower on one throw-away item whose embedding is gathered nowhere, so
+                # that its backward -- and the per-layer gradient all-reduces the other ranks are issuing -- takes
+                # place, with exactly zero gradient
+                real = ids_all_np != 0
+                if lens_all is not None:
+                    real &= lens_all > 0
+                enc_slots = np.flatnonzero(real)[:1].astype(plan.my_first_slots.dtype)
+            if enc_slots.size > 0:
+                my_items = items_all[lib.h2d(enc_slots, dev)]
+                E_mine = te(my_items, lens_all[enc_slots] if (single and lens_all is not None) else None, prep)
+                pad_idx = np.full(plan.u_max, -1, dtype=np.int32)
+                pad_idx[:n_mine] = np.arange(n_mine, dtype=np.int32)
                 E_pad = ops.GatherRowsFn.apply(E_mine, lib.h2d(pad_idx, dev), adt)   # [u_max, D]
-            else:
+            else:       # the whole global batch is padding: no rank runs its tower, the collectives still pair up
                 E_pad = torch.zeros(plan.u_max, D, device=dev, dtype=adt)
             E_table = par.AllGatherRowsFn.apply(E_pad, dist.group.WORLD)         # ONE all-gather; bwd = reduce-scatter
             score_embs = ops.GatherRowsFn.apply(E_table, lib.h2d(plan.slot_to_row.astype(np.int32), dev), adt)

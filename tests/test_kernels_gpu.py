@@ -38,6 +38,32 @@ def test_gemm_layouts(lib, dt, x3, tol, a_mn, b_mn):
             assert r < tol, (M, N, K, r)
 
 
+def test_gemm_opt_in_schedulers():
+    """the two opt-in variants of the CTA-pair kernel (dynamic work-item scheduling, four-CTA cluster with B multicast)
+    give the same results as the default; the switches are read once per process, hence the subprocess"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import torch\n"
+        "from idvs.morec_b200 import lib\n"
+        "for (M, N, K, a_mn, b_mn) in [(6296, 768, 192, False, False), (3072, 768, 2056, True, True), (2048, 1024, 512, False, True)]:\n"
+        "    torch.manual_seed(M)\n"
+        "    A = torch.randn((K, M) if a_mn else (M, K), device='cuda').half()\n"
+        "    B = torch.randn((K, N) if b_mn else (N, K), device='cuda').half()\n"
+        "    C = torch.full((M, N), float('nan'), device='cuda')\n"
+        "    for _ in range(3):\n"
+        "        lib.gemm(A, B, C, M=M, N=N, K=K, lda=A.stride(0), ldb=B.stride(0), ldc=N, a_mn=a_mn, b_mn=b_mn)\n"
+        "    a = A.double().t() if a_mn else A.double()\n"
+        "    b = B.double().t() if b_mn else B.double()\n"
+        "    r = float((C.double() - a @ b.t()).abs().max() / (a @ b.t()).abs().max())\n"
+        "    assert r < 1e-4, (M, N, K, r)\n"
+        "print('ok')\n")
+    for env in ({"MOREC_GEMM_DYN": "1"}, {"MOREC_GEMM_CL4": "1"}, {"MOREC_GEMM_DYN": "1", "MOREC_SIDE_STREAM": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
+
+
 def _epilogue_checks(lib, dt, tol):
     import torch.nn.functional as F
     torch.manual_seed(3)

@@ -35,7 +35,7 @@ def _build(seed, N, T, D, L, dev):
     return a, bert
 
 
-def _worker(rank, world, port, q, use_wrap):
+def _worker(rank, world, port, q, use_wrap, host_plan=False, one_item=False):
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
     from idvs.morec_b200.model import Model
@@ -48,9 +48,17 @@ def _worker(rank, world, port, q, use_wrap):
     try:
         B, L, N, T, D = 6, 8, 40, 12, 64
         full = synth_batch(world * B, L, N, T, seed=77, modal=True, n_users_pop=100, vocab_lo=10, vocab_hi=900)
+        if one_item:      # every real slot holds the SAME item: n_unique = 1 < G, rank 1 owns no item of the global batch
+            flat = full["ids"].reshape(-1)
+            k = int(torch.nonzero(flat)[0])
+            real = flat != 0
+            full["items"][real] = full["items"][k].clone()
+            flat[real] = int(flat[k])
         a, bert = _build(5, N, T, D, L, dev)
         model = Model(a, N, True, bert, full["pop_prob"].numpy()).to(dev).eval()
         model.parallel_mode = "global"
+        if host_plan:     # the step is planned from host ids + the catalogue's token counts: no device->host wait
+            model.set_item_content(full["item_content"])
         if use_wrap:      # tower gradients averaged layer by layer inside its backward (ops._GradSync), rest by DDP
             from idvs.morec_b200.parallel import wrap_ddp
             ddp = wrap_ddp(model, rank)
@@ -59,7 +67,7 @@ def _worker(rank, world, port, q, use_wrap):
         sl = slice(rank * B, (rank + 1) * B)
         ids, lm = full["ids"][sl].to(dev), full["log_mask"][sl].to(dev)
         items = full["items"].view(world * B, L + 1, -1)[sl].reshape(B * (L + 1), -1).to(dev)
-        loss = ddp(ids.reshape(-1), items, lm, rank)
+        loss = ddp(ids.reshape(-1), items, lm, rank, host_ids=full["ids"][sl].numpy() if host_plan else None)
         loss.backward()
         mean_loss = loss.detach().clone()
         dist.all_reduce(mean_loss)
@@ -88,16 +96,19 @@ def _worker(rank, world, port, q, use_wrap):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("use_wrap", [False, True])
-def test_global_mode_two_gpus_equals_single_process(use_wrap):
+@pytest.mark.parametrize("use_wrap,host_plan,one_item", [(False, False, False), (True, False, False), (True, True, False),
+                                                         (True, True, True), (True, False, True)])
+def test_global_mode_two_gpus_equals_single_process(use_wrap, host_plan, one_item):
+    """host_plan: ids exchanged between the hosts (gloo), no device->host wait in the step.  one_item: a rank that owns
+    no distinct item of the global batch still issues every gradient collective (formerly a hang)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, use_wrap)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, use_wrap, host_plan, one_item)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=120)
     for rank, ok, msg in res:
