@@ -38,12 +38,18 @@ BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_at
                  max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12)
 CFG = dict(B=64, L=25, T=30, D=512, heads=2, blocks=2, N=50000, drop=0.1,
            lr=1e-4, fine_tune_lr=5e-5, l2=0.01, fine_tune_l2=0.01)      # train_bert_base.py:22-28
+# BASELINE.json configs[1]: SASRec + BERT-tiny, titles of 128 word pieces (run.py:55-57: H=128, 2 layers, 2 heads, I=512)
+BERT_TINY = dict(BERT_BASE, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512)
+CFG_TINY = dict(CFG, T=128)
 # BASELINE.json configs[3]: SASRec + Swin-T, HM-shape synthetic 3x224x224, B=32, L=10 (V/parameters.py:38), D=512
 SWIN_T = dict(image_size=224, patch_size=4, num_channels=3, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
               window_size=7, mlp_ratio=4.0, qkv_bias=True, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
               drop_path_rate=0.1, hidden_act="gelu", layer_norm_eps=1e-5)
 CFG_VISION = dict(B=32, L=10, T=0, D=512, heads=2, blocks=2, N=50000, drop=0.1,
                   lr=1e-4, fine_tune_lr=1e-4, l2=0.1, fine_tune_l2=0.1)    # train_swin_tiny.py
+# BASELINE.json configs[4]: SASRec + Swin-B, B=16 per GPU
+SWIN_B = dict(SWIN_T, embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32])
+CFG_VISION_B = dict(CFG_VISION, B=16)
 
 
 # DRAM traffic of the dominant kernel from one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum
@@ -60,7 +66,9 @@ def make_args(cfg):
     a.max_seq_len = cfg["L"]; a.embedding_dim = cfg["D"]; a.num_attention_heads = cfg["heads"]
     a.drop_rate = cfg["drop"]; a.transformer_block = cfg["blocks"]; a.num_words_title = cfg["T"]
     a.num_words_abstract = 50; a.num_words_body = 50; a.news_attributes = ["title"]
-    a.bert_model_load = "bert_base_uncased"; a.word_embedding_dim = 768
+    tiny = cfg.get("bert") is BERT_TINY
+    a.bert_model_load = "bert_tiny" if tiny else "bert_base_uncased"
+    a.word_embedding_dim = 128 if tiny else 768
     return a
 
 
@@ -133,7 +141,7 @@ def cpu_oracle_step_fn(cfg, B_sample, seed):
     torch.manual_seed(seed)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    bert = BertModel(BertConfig(**BERT_BASE))
+    bert = BertModel(BertConfig(**cfg.get("bert", BERT_BASE)))
     sd = {("bert_encoder.text_encoders.title.bert_model." + k): v for k, v in bert.state_dict().items()}
     D, L = cfg["D"], cfg["L"]
     g = torch.Generator().manual_seed(seed)
@@ -230,7 +238,7 @@ def reference_step_fn(cfg, B, seed, root):
     from idvs.morec_b200.synth import synth_batch
     RefModel = load_reference_model_cls(root)
     torch.manual_seed(seed)
-    bert = BertModel(BertConfig(**BERT_BASE))
+    bert = BertModel(BertConfig(**cfg.get("bert", BERT_BASE)))
     for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
         if i in (197, 198):
             p.requires_grad = False
@@ -320,14 +328,15 @@ def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, p
     from idvs.morec_b200.synth import synth_batch
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(12345)
-    net = SwinForImageClassification(SwinConfig(**SWIN_T))
+    net = SwinForImageClassification(SwinConfig(**cfg.get("swin", SWIN_T)))
     net.classifier = torch.nn.Linear(net.classifier.in_features, cfg["D"])          # V/run.py:49-54
     torch.nn.init.xavier_normal_(net.classifier.weight.data)
     torch.nn.init.constant_(net.classifier.bias.data, 0)
     batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], 0, 777 + 1000 * rank + i, modal=False, mind_shape=False)
                for i in range(n_batches)]
     a = types.SimpleNamespace(max_seq_len=cfg["L"], embedding_dim=cfg["D"], num_attention_heads=cfg["heads"],
-                              drop_rate=cfg["drop"], transformer_block=cfg["blocks"], CV_model_load="swin_tiny")
+                              drop_rate=cfg["drop"], transformer_block=cfg["blocks"],
+                              CV_model_load="swin_base" if cfg.get("swin") is SWIN_B else "swin_tiny")
     from idvs.morec_b200.synth import pop_from_batches
     model = Model(a, cfg["N"], True, net, pop_from_batches(batches).numpy()).to(dev)
     model.set_compute_dtype(mode)
@@ -347,11 +356,18 @@ def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, p
     resident = [(a_.to(dev), b_.to(dev), c_.to(dev)) for (a_, b_, c_) in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 14)      # fp16 storage: dynamic loss scaling (V/run.py:186, 213-215)
+
     def step(ids, items, lm):
         opt.zero_grad(set_to_none=True)
         loss = model_run(ids.view(-1), items, lm, local_rank)
-        loss.backward()
-        opt.step()
+        if model.compute_dtype == "fp16":
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        else:
+            loss.backward()
+            opt.step()
         return loss
 
     return step, host, resident, h2d_bytes
@@ -367,9 +383,10 @@ def setup_training(cfg, mode, n_batches, rank=0, world=1, local_rank=0, parallel
     from idvs.morec_b200.synth import synth_batch
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(12345)
-    bert = BertModel(BertConfig(**BERT_BASE))
-    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:73-75 (freeze_paras_before=0; pooler frozen)
-        if i in (197, 198):
+    bert = BertModel(BertConfig(**cfg.get("bert", BERT_BASE)))
+    pooler = (37, 38) if cfg.get("bert") is BERT_TINY else (197, 198)
+    for i, (n, p) in enumerate(bert.named_parameters()):          # run.py:55-75 (freeze_paras_before=0; pooler frozen)
+        if i in pooler:
             p.requires_grad = False
     from idvs.morec_b200.synth import pop_from_batches
     batches = [synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * rank + i, modal=True)
@@ -509,8 +526,9 @@ def main():
     ap.add_argument("--no-modes", action="store_true", help="skip the short per-mode throughput block")
     ap.add_argument("--parallel", default="global", choices=["global", "local"],
                     help="multi-GPU semantics for N > 1 (idvs/morec_b200/parallel.py)")
-    ap.add_argument("--workload", default="text", choices=["text", "vision"],
-                    help="text = SASRec+BERT-base (headline, configs[2]); vision = SASRec+Swin-T (configs[3])")
+    ap.add_argument("--workload", default="text", choices=["text", "text_tiny", "vision", "vision_b"],
+                    help="text = SASRec+BERT-base (headline, configs[2]); text_tiny = BERT-tiny, T=128 (configs[1]); "
+                         "vision = SASRec+Swin-T (configs[3]); vision_b = Swin-B, B=16 (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scoring", action="store_true", help="skip the K8 (scoring + CE kernel) roofline block")
     ap.add_argument("--d2h-plan", action="store_true", help="plan each step from a device->host copy of the ids and token "
@@ -525,12 +543,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    vision = args.workload == "vision"
-    cfg = dict(CFG_VISION) if vision else dict(CFG)
-    workload = (f"MoRec SASRec+Swin-T end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, 3x224x224 images, "
-                f"D={cfg['D']}, HM-shape synthetic (BASELINE.json configs[3])") if vision else \
-               (f"MoRec SASRec+BERT-base end2end in-batch debiased CE, B={cfg['B']}/GPU, L={cfg['L']}, T={cfg['T']}, "
-                f"D={cfg['D']}, N={cfg['N']} items, MIND-shape synthetic (BASELINE.json configs[2])")
+    vision = args.workload.startswith("vision")
+    cfg = {"text": dict(CFG, bert=BERT_BASE), "text_tiny": dict(CFG_TINY, bert=BERT_TINY),
+           "vision": dict(CFG_VISION, swin=SWIN_T), "vision_b": dict(CFG_VISION_B, swin=SWIN_B)}[args.workload]
+    workload = (f"MoRec SASRec+Swin-{'B' if args.workload == 'vision_b' else 'T'} end2end in-batch debiased CE, B={cfg['B']}/GPU, "
+                f"L={cfg['L']}, 3x224x224 images, D={cfg['D']}, HM-shape synthetic "
+                f"(BASELINE.json configs[{4 if args.workload == 'vision_b' else 3}])") if vision else \
+               (f"MoRec SASRec+BERT-{'tiny' if args.workload == 'text_tiny' else 'base'} end2end in-batch debiased CE, "
+                f"B={cfg['B']}/GPU, L={cfg['L']}, T={cfg['T']}, D={cfg['D']}, N={cfg['N']} items, MIND-shape synthetic "
+                f"(BASELINE.json configs[{1 if args.workload == 'text_tiny' else 2}])")
 
     if args.impl == "reference":
         if rank != 0:
@@ -720,7 +741,8 @@ def main():
         import numpy as np
         lens = step.model._item_lens
         tok_exec = float(np.mean([int(lens[np.unique(host[W + i][0].numpy())].sum()) for i in range(K)]))
-        Hh, Ii, nl = BERT_BASE["hidden_size"], BERT_BASE["intermediate_size"], BERT_BASE["num_hidden_layers"]
+        bc = cfg.get("bert", BERT_BASE)
+        Hh, Ii, nl = bc["hidden_size"], bc["intermediate_size"], bc["num_hidden_layers"]
         per_tok = nl * 2.0 * (4 * Hh * Hh + 2 * Hh * Ii)           # forward GEMM FLOPs of one token through the tower
         tok_dense = cfg["B"] * (cfg["L"] + 1) * cfg["T"]
         executed = gemm_flops / K
