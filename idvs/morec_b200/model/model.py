@@ -31,6 +31,17 @@ class Model(torch.nn.Module):
     # gradient (measured: tools/diag_bf16.py) while the block is < 0.1 % of the step's FLOPs.
     _CE_META = dict(x3=True)
 
+    def _ce_inputs(self, prec_vec, score_embs):
+        """arithmetic of the scoring + CE kernel per precision mode: `fp32` -> 3xTF32 on fp32 operands (parity mode);
+        `tf32` -> one kind::tf32 pass; `fp16` / `bf16` -> kind::f16 on the 16-bit activations as they are (what the
+        reference's autocast does with `torch.matmul(prec_vec, score_embs.t())`, model.py:49 -- here with fp32
+        accumulation and fp32 logits / softmax).  Column count grows with the number of GPUs in `global` mode, so at
+        8 GPUs the 3xTF32 form cost ~1 ms per step."""
+        mode = getattr(self, "compute_dtype", "fp32")
+        if mode in ("fp16", "bf16") and prec_vec.dtype == score_embs.dtype and prec_vec.dtype != torch.float32:
+            return dict(x3=False), prec_vec, score_embs
+        return dict(x3=(mode != "tf32")), prec_vec.float(), score_embs.float()
+
     def __init__(self, args, item_num, use_modal, bert_model, pop_prob_list):
         super().__init__()
         self.args = args
@@ -192,8 +203,8 @@ class Model(torch.nn.Module):
         # in-batch debiased CE (model.py:45-67)
         lm = log_mask.to(torch.float32).contiguous()
         member, pad = lib.inbatch_mask(sample_items_id.reshape(B, L + 1).contiguous(), ids_flat.contiguous(), B, L)
-        loss, _ = ops.InbatchCEFn.apply(self._CE_META, prec_vec.float(), score_embs.float(), member, pad, log_pop_c,
-                                        lm.reshape(-1), B, L, 0, None)
+        ce_meta, P_ce, E_ce = self._ce_inputs(prec_vec, score_embs)
+        loss, _ = ops.InbatchCEFn.apply(ce_meta, P_ce, E_ce, member, pad, log_pop_c, lm.reshape(-1), B, L, 0, None)
         return loss
 
     # -------------------------------------------------------------------------------------------
@@ -281,8 +292,9 @@ class Model(torch.nn.Module):
         dist.all_reduce(n_valid)                                                   # global valid-row count
         member, pad = lib.inbatch_mask(sample_items_id.reshape(B, L + 1).contiguous(), ids_all.contiguous(), B, L)
         log_pop_c = self._log_pop[ids_all].contiguous()
-        loss, _ = ops.InbatchCEFn.apply(self._CE_META, prec_vec.float(), score_embs.float(), member, pad,
-                                        log_pop_c, lm.reshape(-1), B, L, rank * C, n_valid)
+        ce_meta, P_ce, E_ce = self._ce_inputs(prec_vec, score_embs)
+        loss, _ = ops.InbatchCEFn.apply(ce_meta, P_ce, E_ce, member, pad, log_pop_c, lm.reshape(-1), B, L, rank * C,
+                                        n_valid)
         # x G: DistributedDataParallel averages gradients over the G ranks; the objective is the SUM of the per-rank
         # partial losses (each already divided by the global valid-row count)
         return loss * float(G)

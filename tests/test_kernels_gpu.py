@@ -355,6 +355,51 @@ def test_inbatch_ce_fwd_bwd_vs_oracle(lib, B, L, D, hi):
     assert float(Pc.grad[inval.cuda()].abs().max()) == 0.0 if inval.any() else True
 
 
+@pytest.mark.parametrize("dt,x3,tol_l,tol_g", [(torch.float32, False, 5e-3, 2e-2), (torch.float16, False, 1e-3, 1e-2),
+                                               (torch.bfloat16, False, 2e-2, 8e-2)])
+@pytest.mark.parametrize("B,L,D,G", [(64, 25, 512, 1), (16, 25, 512, 4), (6, 8, 64, 1)])
+def test_inbatch_ce_fast_arithmetic(lib, dt, x3, tol_l, tol_g, B, L, D, G):
+    """the scoring + CE kernel in the arithmetic of the fast modes (one TF32 pass / f16 / bf16 operands, fp32
+    accumulation, logits and softmax) -- incl. the CTA-pair kernel path wide column counts take and the column offset
+    of the `global` multi-GPU mode (rows of rank 1 against G*C columns) -- vs the fp64 oracle on the SAME rounded inputs"""
+    from oracle import morec_oracle as O
+    from idvs.morec_b200 import ops
+    torch.manual_seed(B * L + G)
+    ids_all = torch.randint(1, 3000, (G * B, L + 1))
+    for b in range(G * B):
+        ids_all[b, :int(torch.randint(0, L - 1, (1,)))] = 0
+    r = G - 1                                                 # the rank whose rows are scored
+    ids = ids_all[r * B:(r + 1) * B]
+    lm = O.log_mask_from_ids(ids)
+    C = B * (L + 1)
+    P = (torch.randn(B * L, D) * 0.3).to(dt)
+    E = (torch.randn(G * C, D) * 0.3).to(dt)
+    pop = torch.rand(3000) + 0.01
+    pop[0] = 1.0
+    logp = torch.log(pop.float()[ids_all.reshape(-1)])
+    # fp64 restatement with global columns: S = P E^T - log p, reject mask from the local user's ids, targets offset by r*C
+    Pd, Ed = P.double().requires_grad_(True), E.double().requires_grad_(True)
+    S = Pd @ Ed.t() - logp.double()[None, :]
+    colid = ids_all.reshape(-1)
+    rows_user = torch.arange(B * L) // L
+    tgt = r * C + rows_user * (L + 1) + (torch.arange(B * L) % L) + 1
+    member = (colid[None, None, :] == ids[:, :, None]).any(1)                 # [B, G*C]
+    masked = (colid == 0)[None, :] | member[rows_user]
+    masked[torch.arange(B * L), tgt] = False
+    S = torch.where(masked, torch.full_like(S, -1e4), S)
+    valid = lm.reshape(-1) != 0
+    loss_o = torch.nn.functional.cross_entropy(S[valid], tgt[valid])
+    loss_o.backward()
+    Pc, Ec = P.cuda().requires_grad_(True), E.cuda().requires_grad_(True)
+    mem, pad = lib.inbatch_mask(ids.cuda(), colid.cuda(), B, L)
+    loss, sum_cnt = ops.InbatchCEFn.apply(dict(x3=x3), Pc, Ec, mem, pad, logp.cuda(), lm.reshape(-1).cuda(), B, L, r * C, None)
+    assert int(sum_cnt[1]) == int(valid.sum())
+    assert abs(float(loss) - float(loss_o)) < tol_l, (float(loss), float(loss_o))
+    loss.backward()
+    assert rel(Pc.grad.float().cpu(), Pd.grad) < tol_g and rel(Ec.grad.float().cpu(), Ed.grad) < tol_g
+    assert float(Ec.grad[(colid == 0).cuda()].abs().max()) == 0.0
+
+
 def test_adamw_multi_matches_torch(lib):
     import ctypes
     torch.manual_seed(10)
