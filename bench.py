@@ -340,6 +340,7 @@ def setup_training_vision(cfg, mode, n_batches, rank=0, world=1, local_rank=0, p
     from idvs.morec_b200.synth import pop_from_batches
     model = Model(a, cfg["N"], True, net, pop_from_batches(batches).numpy()).to(dev)
     model.set_compute_dtype(mode)
+    model.item_dedup = "always"      # north star: "forward over the batch's unique items"
     model.parallel_mode = "local" if world > 1 else parallel     # (global mode exchanges token rows; images stay local)
     model.train()
     if world > 1:
@@ -595,8 +596,9 @@ def main():
     # ---------------- device-resident throughput (`value`): K steps, batches already in HBM
     # warm-up: W steps, the first one on the batch with the most real tokens so the allocator reaches its
     # steady-state footprint before anything is timed
-    if vision:
-        big = 0
+    if vision:  # activation sizes follow the number of DISTINCT images of a step
+        import numpy as np
+        big = max(range(len(host)), key=lambda i: int(np.unique(host[i][0].numpy()).size))
     else:       # packed token count of a step = tokens of the batch's DISTINCT items
         import numpy as np
         lens = step.model._item_lens

@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(BIG ? 512 : 256, BIG ? 1 : 3) ln_bwd_kernel(co
     if (act) {
         gam = *reinterpret_cast<const float4*>(p.gamma + 4 * c);
         bet = *reinterpret_cast<const float4*>(p.beta + 4 * c);
-        ig = make_float4(1.f / gam.x, 1.f / gam.y, 1.f / gam.z, 1.f / gam.w);
+        // xhat is rebuilt as (y - beta) / gamma; a gamma of exactly 0 carries no xhat information (its column then
+        // contributes nothing to dx either, dy * gamma = 0): treat xhat as 0 there instead of producing inf / NaN
+        ig = make_float4(gam.x != 0.f ? 1.f / gam.x : 0.f, gam.y != 0.f ? 1.f / gam.y : 0.f,
+                         gam.z != 0.f ? 1.f / gam.z : 0.f, gam.w != 0.f ? 1.f / gam.w : 0.f);
     }
     const T* dyb = reinterpret_cast<const T*>(p.dy);
     const T* dy2b = reinterpret_cast<const T*>(p.dy2);

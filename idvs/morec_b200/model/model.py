@@ -296,5 +296,16 @@ class Model(torch.nn.Module):
         loss, _ = ops.InbatchCEFn.apply(ce_meta, P_ce, E_ce, member, pad, log_pop_c, lm.reshape(-1), B, L, rank * C,
                                         n_valid)
         # x G: DistributedDataParallel averages gradients over the G ranks; the objective is the SUM of the per-rank
-        # partial losses (each already divided by the global valid-row count)
+        # partial losses (each already divided by the global valid-row count).  The returned value is therefore G x this
+        # rank's share of the global mean CE -- for logging use global_mean_loss().
+        self._last_partial_loss = loss.detach()
         return loss * float(G)
+
+    def global_mean_loss(self):
+        """mean CE over the valid rows of the whole global batch of the last `global`-mode step (one scalar all-reduce;
+        the number a log line should show -- forward() returns G x the rank's partial sum so that DDP's gradient
+        averaging reproduces the single-process gradient)"""
+        import torch.distributed as dist
+        v = self._last_partial_loss.clone()
+        dist.all_reduce(v)
+        return v

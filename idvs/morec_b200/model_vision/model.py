@@ -35,6 +35,16 @@ class Model(_TextModel):
         self.compute_dtype = getattr(args, "compute_dtype", "fp32")
         self.set_compute_dtype(self.compute_dtype)
 
+    # the gradient-sync flags of the text Model (its ops._GradSync only covers the BERT tower); images are never
+    # exchanged between ranks, so the vision Model always runs the reference's DDP semantics
+    _overlap_grad_sync = False
+    _grad_sync_suspended = False
+
+    def forward(self, sample_items_id, sample_items, log_mask, local_rank, host_ids=None):
+        if self.use_modal and self.parallel_mode == "global":
+            self.parallel_mode = "local"
+        return super().forward(sample_items_id, sample_items, log_mask, local_rank, host_ids)
+
     def set_compute_dtype(self, name):
         from ..model.encoders import COMPUTE_DTYPES
         assert name in COMPUTE_DTYPES, name
@@ -56,7 +66,12 @@ class Model(_TextModel):
         else:
             ids_np = lib.d2h_many([ids_flat])[0]
         nz = np.nonzero(ids_np)[0]
-        if self.item_dedup == "slots":
+        # 'auto' (the text Model's rule): duplicates are encoded once only when that is exact -- under stochastic depth
+        # (training, drop_path_rate > 0) the reference draws an independent mask per slot, so every slot is encoded;
+        # 'always' shares one mask between the duplicates of a step (what bench.py measures), 'slots' never dedups
+        cfgv = getattr(getattr(self.cv_encoder, "image_net", None), "config", None)
+        stochastic = self.training and float(getattr(cfgv, "drop_path_rate", 0.0) or 0.0) > 0.0
+        if self.item_dedup == "slots" or (self.item_dedup == "auto" and stochastic):
             rows = nz
             s2u = np.full(ids_np.size, -1, dtype=np.int32)
             s2u[nz] = np.arange(nz.size, dtype=np.int32)
