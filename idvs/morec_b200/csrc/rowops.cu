@@ -313,7 +313,20 @@ __global__ void __launch_bounds__(256) grad_check_kernel(const AdamTensor* __res
         const AdamTensor ch = tensors[t];
         const int e0 = (ci - chunk_start[t]) * ADAM_CHUNK;
         const int e1 = min(ch.n, e0 + ADAM_CHUNK);
-        for (int i = e0 + threadIdx.x; i < e1; i += blockDim.x) bad |= !(fabsf(ch.g[i]) <= 3.0e38f);
+        // float4 loads, four independent ones in flight per thread (the scalar loop with its dependent `bad |=` chain
+        // read at 2.1 TB/s: 211 us for the 440 MB gradient set); gradients are 16-byte aligned as in adamw_multi_kernel
+        int i = e0 + threadIdx.x * 4;
+        for (; i + 3 * 1024 + 4 <= e1; i += 4 * 1024) {
+            const float4 a = *reinterpret_cast<const float4*>(ch.g + i);
+            const float4 b = *reinterpret_cast<const float4*>(ch.g + i + 1024);
+            const float4 c = *reinterpret_cast<const float4*>(ch.g + i + 2048);
+            const float4 d = *reinterpret_cast<const float4*>(ch.g + i + 3072);
+#define MOREC_BAD4(q) (!(fabsf(q.x) <= 3.0e38f) | !(fabsf(q.y) <= 3.0e38f) | !(fabsf(q.z) <= 3.0e38f) | !(fabsf(q.w) <= 3.0e38f))
+            bad |= MOREC_BAD4(a) | MOREC_BAD4(b) | MOREC_BAD4(c) | MOREC_BAD4(d);
+#undef MOREC_BAD4
+        }
+        for (; i < e1; i += 1024)
+            for (int k = i; k < min(i + 4, e1); ++k) bad |= !(fabsf(ch.g[k]) <= 3.0e38f);
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.f;
 }
