@@ -612,15 +612,20 @@ def main():
             def share_tokens(i):
                 ids_all = np.concatenate([synth_batch(cfg["B"], cfg["L"], cfg["N"], cfg["T"], 12345 + 1000 * r + i,
                                                       modal=False)["ids"].numpy().reshape(-1) for r in range(world)])
-                worst = 0
+                worst, n_unique = 0, 0
                 for r in range(world):
                     pl = plan_global_batch(ids_all, world, r)
                     worst = max(worst, int(lens[ids_all[pl.my_first_slots]].sum()))
-                return worst
-            big = max(range(len(host)), key=share_tokens)
+                    n_unique = pl.n_unique
+                return worst, n_unique
+            shares = [share_tokens(i) for i in range(len(host))]
+            big = max(range(len(host)), key=lambda i: shares[i][0])
+            big2 = max(range(len(host)), key=lambda i: shares[i][1])     # most distinct items: largest all-gather buffers
         else:
             big = max(range(len(host)), key=lambda i: int(lens[np.unique(host[i][0].numpy())].sum()))
     step(*resident[big])
+    if not vision and world > 1 and args.parallel == "global":
+        step(*resident[big2])
     for i in range(W - 1):
         step(*resident[i])
     sync()
