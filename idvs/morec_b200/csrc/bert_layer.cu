@@ -198,3 +198,18 @@ extern "C" int morec_bert_layers_bwd(const MorecBertLayerBwd* layers, int n_laye
     for (int l = 0; l < n_layers; ++l) RUN(bert_layer_bwd_impl(layers + l, stream, l == n_layers - 1));
     return MOREC_OK;
 }
+
+extern "C" int morec_bert_layers_bwd_ex(const MorecBertLayerBwd* layers, int n_layers, int join, void* stream) {
+    MOREC_CHECK_ARG((layers || n_layers == 0) && n_layers >= 0, "bert_layers_bwd_ex: null args");
+    for (int l = 0; l < n_layers; ++l) RUN(bert_layer_bwd_impl(layers + l, stream, join && l == n_layers - 1));
+    if (n_layers == 0 && join) {               // join only: order `stream` after whatever the side stream still holds
+        SideCtx* sc = side_ctx();
+        if (sc)
+            for (int k = 0; k < 4; ++k)
+                if (sc->pending[k]) {
+                    MOREC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, sc->done[k], 0));
+                    sc->pending[k] = false;
+                }
+    }
+    return MOREC_OK;
+}

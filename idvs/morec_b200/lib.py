@@ -66,6 +66,7 @@ def load():
         "morec_bce_bwd": [P, P, P, P, P, P, P, P, I, I, I, P, P, P, P],
         "morec_bert_layers_fwd": [P, I, P],
         "morec_bert_layers_bwd": [P, I, P],
+        "morec_bert_layers_bwd_ex": [P, I, I, P],
         "morec_bert_layer_fwd": [P, P],
         "morec_bert_layer_bwd": [P, P],
     }
@@ -748,12 +749,15 @@ def bert_layers_fwd(rec):
     _LAUNCHES += _N_LAYER_FWD_LAUNCHES * rec.shape[0] - 1
 
 
-def bert_layers_bwd(rec):
-    """rec: numpy array of LAYER_BWD_DT records in execution order (last layer first)"""
+def bert_layers_bwd(rec, join=True):
+    """rec: numpy array of LAYER_BWD_DT records in execution order (last layer first), or None (join only).
+    join=False leaves the last record's weight-gradient work in flight on the side stream (see the header)"""
     global _LAUNCHES
-    rc = load().morec_bert_layers_bwd(rec.ctypes.data, rec.shape[0], _stream())
-    _check(rc, "morec_bert_layers_bwd")
-    _LAUNCHES += _N_LAYER_BWD_LAUNCHES * rec.shape[0] - 1
+    n = 0 if rec is None else rec.shape[0]
+    rc = load().morec_bert_layers_bwd_ex(rec.ctypes.data if n else None, n, int(join), _stream())
+    _check(rc, "morec_bert_layers_bwd_ex")
+    if n:
+        _LAUNCHES += _N_LAYER_BWD_LAUNCHES * n - 1
 
 
 def clock_probe(out):

@@ -716,10 +716,19 @@ class BertTowerFn(torch.autograd.Function):
         if sync is None:
             lib.bert_layers_bwd(recb)
         else:
-            for k in range(n_layers):                            # this layer's gradients: all-reduce while the layers below run
-                lib.bert_layers_bwd(recb[k:k + 1])
-                arena.off = lay.layer_end[int(order[k])]
-                sync.flush()
+            # a layer's gradients are all-reduced while the layers below run.  Its weight gradients are produced on the
+            # library's side stream; the main stream is ordered after them once the NEXT layer has been enqueued (that
+            # layer waits for every scratch buffer the side work reads), so the collective of layer k is issued one
+            # layer late instead of joining the two streams after every layer (which serialised them: the 2-GPU step
+            # gained nothing from the side stream)
+            for k in range(n_layers):
+                lib.bert_layers_bwd(recb[k:k + 1], join=False)
+                if k >= 1:
+                    arena.off = lay.layer_end[int(order[k - 1])]
+                    sync.flush()
+            lib.bert_layers_bwd(None, join=True)
+            arena.off = lay.layer_end[int(order[n_layers - 1])]
+            sync.flush()
         last = int(order[-1]) & 1
         dx, dx2 = pp[2 * last], pp[2 * last + 1]
         # ---- embeddings backward: y = dropout(LN(z)), z = word + pos + type

@@ -285,6 +285,12 @@ int morec_bert_layer_bwd(const MorecBertLayerBwd* args, void* stream);
 /* several layers per call: HOST arrays of records in execution order (backward: last layer first) */
 int morec_bert_layers_fwd(const MorecBertLayerFwd* layers, int n_layers, void* stream);
 int morec_bert_layers_bwd(const MorecBertLayerBwd* layers, int n_layers, void* stream);
+/* The same, with control over the final join: join = 0 leaves the weight-gradient work of the LAST record in flight on
+ * the library's side stream when the call returns.  `stream` is ordered after that work by the time the NEXT record
+ * (of a following call) has been enqueued, or by a following call with join = 1 (n_layers may be 0: join only).  Lets
+ * a multi-GPU caller interleave per-layer gradient collectives with the layers without serialising the two streams
+ * at every layer (hot path of inbatch_sasrec_e2e_text/run.py:148 + model/encoders.py:68 under DistributedDataParallel). */
+int morec_bert_layers_bwd_ex(const MorecBertLayerBwd* layers, int n_layers, int join, void* stream);
 
 #ifdef __cplusplus
 }
