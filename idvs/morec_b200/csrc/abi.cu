@@ -4,6 +4,8 @@
 #include "../../../include/morec_b200.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace morec {
 static thread_local char g_err[512] = "";
 void set_last_error(const char* fmt, ...) {
@@ -20,6 +22,10 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
     cached = n;
     return n;
+}
+bool pdl_enabled() {
+    static const bool v = []() { const char* e = getenv("MOREC_PDL"); return !(e && e[0] == '0'); }();
+    return v;
 }
 }  // namespace morec
 

@@ -157,6 +157,8 @@ __device__ __forceinline__ void tc16_smT_dot_cols(const T* Sm, const T* Y, int j
 
 template <typename T, int D, int LP>
 __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(const TcAttnParams p) {
+    pdl_wait();
+    pdl_trigger();
     using C = Tc16Cfg<D, LP>;
     extern __shared__ __align__(16) uint8_t tc16_smem[];
     T* Qs = reinterpret_cast<T*>(tc16_smem);
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_fwd_kernel(
 
 template <typename T, int D, int LP>
 __global__ void __launch_bounds__(Tc16Cfg<D, LP>::THREADS) attn_tc16_bwd_kernel(const TcAttnParams p) {
+    pdl_wait();
+    pdl_trigger();
     using C = Tc16Cfg<D, LP>;
     extern __shared__ __align__(16) uint8_t tc16_smem[];
     T* Qs = reinterpret_cast<T*>(tc16_smem);
@@ -317,7 +321,7 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
             MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set_f = smem;
         }
-        kern<<<grid, C::THREADS, smem, stream>>>(p);
+        MOREC_CUDA(launch_pdl(kern, grid, dim3(C::THREADS), smem, stream, p));
     } else {
         auto kern = attn_tc16_bwd_kernel<T, D, LP>;
         static size_t set_b = 0;
@@ -325,7 +329,7 @@ static int tc16_launch(const TcAttnParams& p, bool bwd, cudaStream_t stream) {
             MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             set_b = smem;
         }
-        kern<<<grid, C::THREADS, smem, stream>>>(p);
+        MOREC_CUDA(launch_pdl(kern, grid, dim3(C::THREADS), smem, stream, p));
     }
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;

@@ -1,5 +1,6 @@
 // Shared device/host helpers for the morec_b200 C-ABI library (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -37,6 +38,29 @@ void set_last_error(const char* fmt, ...);
 #define MOREC_LAUNCH_CHECK() MOREC_CUDA(cudaGetLastError())
 
 int num_sms();
+
+// ---- programmatic dependent launch (on by default; MOREC_PDL=0 disables) ---------------------------------------
+// The kernels of the BERT tower sequence (GEMMs, LayerNorm, 16-bit attention, column sums: ~290 of a step's ~320
+// launches) begin with pdl_wait() -- griddepcontrol.wait: block until every prerequisite grid has completed and its
+// memory is visible; a no-op for a normal launch -- followed by pdl_trigger().  Launched through launch_pdl() with the
+// programmatic-stream-serialization attribute, the NEXT kernel of the stream is set up (and its CTAs made resident as
+// SMs free up) while the current one still runs, so the launch latency between dependent kernels is hidden; all
+// reads and writes of a kernel still happen after its predecessor has finished.  Measured: 10.61 -> 10.46 ms per
+// BERT-base step (A/B twice on one box).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // Storage dtype codes of the C ABI: 0 = fp32, 1 = bf16, 3 = fp16 (2 = fp32 storage with 3xTF32 GEMM math; it only
 // differs from 0 inside morec_gemm).  MOREC_DISPATCH_T runs the statement with `T` bound to the element type.

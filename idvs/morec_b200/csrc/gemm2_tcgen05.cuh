@@ -272,6 +272,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                               // (barriers, TMEM and descriptor prefetch above overlap the predecessor's tail)
+    pdl_trigger();
 
     const int pair = blockIdx.x / CL;             // work is dealt to clusters; the pairs of a cluster share (n-tile, split)
     const int n_pairs = gridDim.x / CL;
@@ -581,10 +583,12 @@ int gemm2_launch_cl(const GemmArgs& g, const typename Epi::Params& ep, cudaStrea
     cfg.blockDim = dim3(gemm2_threads<Epi>(), 1, 1);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute la[1];
+    cudaLaunchAttribute la[2];
     la[0].id = cudaLaunchAttributeClusterDimension;
     la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-    cfg.attrs = la; cfg.numAttrs = 1;
+    la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = la; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MOREC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p, ep));
     return MOREC_OK;
 }

@@ -318,6 +318,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
 
     const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
@@ -556,8 +558,7 @@ int gemm_launch(const GemmArgs& g, const typename Epi::Params& ep, cudaStream_t 
         MOREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmC2, p, ep);
-    MOREC_LAUNCH_CHECK();
+    MOREC_CUDA(launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmC, tmC2, p, ep));
     return MOREC_OK;
 }
 

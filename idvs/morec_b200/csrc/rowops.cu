@@ -156,6 +156,8 @@ __global__ void mean_rows_kernel(const T* __restrict__ x, T* __restrict__ out, i
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
                                                      int ld, int rows_per_cta) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float4 red[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + tx) * 4;
@@ -461,7 +463,7 @@ extern "C" int morec_colsum(const void* x, float* out, int M, int N, int ld, int
     if (rows_per < 64) rows_per = 64;
     gy = (M + rows_per - 1) / rows_per;
     dim3 grid(gx, gy);
-    MOREC_DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, out, M, N, ld, rows_per)));
+    MOREC_DISPATCH_T(dtype, MOREC_CUDA(launch_pdl(colsum_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, (const T*)x, out, M, N, ld, rows_per)));
     MOREC_LAUNCH_CHECK();
     return MOREC_OK;
 }

@@ -58,7 +58,7 @@ def test_gemm_opt_in_schedulers():
         "    r = float((C.double() - a @ b.t()).abs().max() / (a @ b.t()).abs().max())\n"
         "    assert r < 1e-4, (M, N, K, r)\n"
         "print('ok')\n")
-    for env in ({"MOREC_GEMM_DYN": "1"}, {"MOREC_GEMM_CL4": "1"}, {"MOREC_GEMM_DYN": "1", "MOREC_SIDE_STREAM": "0"}):
+    for env in ({"MOREC_GEMM_DYN": "1"}, {"MOREC_GEMM_CL4": "1"}, {"MOREC_GEMM_DYN": "1", "MOREC_PDL": "0"}):
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
