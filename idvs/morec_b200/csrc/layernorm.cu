@@ -243,6 +243,10 @@ extern "C" int morec_layernorm_fwd(const void* x, const void* residual, const fl
     if (M <= 0) return MOREC_OK;
     LnFwdParams p{x, residual, pos, pos_period > 0 ? pos_period : 1, gamma, beta, y, y_pre, rstd, M, H, eps,
                   p_pre, p_post, seed, off_pre, off_post};
+    // Grid: up to 8 CTAs per SM although only 4 are resident (62 registers): measured on B200 at 12,037 x 768, the
+    // resulting two waves of short-lived CTAs (18.9 us) beat an occupancy-sized persistent grid (21.4 us) and register
+    // caps for 5 / 6 resident CTAs (22.4 / 24.9 us, spills) -- the block scheduler's refill balances better than a
+    // fixed row stride.
     int blocks = (M + LN_WARPS - 1) / LN_WARPS;
     const int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
