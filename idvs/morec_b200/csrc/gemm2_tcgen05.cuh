@@ -101,8 +101,9 @@ __device__ __forceinline__ void st_shared_cluster_u32(uint32_t local_addr, uint3
 // than the ~1,700 cycles by which the operand ring (6 stages, ~2,900 cycles TMA latency under load) is ahead of the
 // tensor core -- measured 51.4 -> 56.9 us at 12037 x 3072 x 768 with the producer as scheduler.
 // A pair whose CTAs became resident late (the SMs were held by an NCCL kernel or by a GEMM of the other stream) simply
-// takes fewer items; with the static `w += n_pairs` deal such a pair ran its whole share after everybody else had
-// finished (measured: GEMM time per step 7.10 -> 7.75 ms with the gradient all-reduce of a 2-GPU run alongside).
+// takes fewer items; with the static `w += n_pairs` deal such a pair runs its whole share after everybody else has
+// finished.  OPT-IN (gemm_sched_slot() in gemm_tcgen05.cu has the measurements: free in isolation, no gain next to
+// NCCL's kernels on 2 GPUs except when the collective is squeezed onto 2 CTAs, where it recovers 0.46 ms per step).
 constexpr int kSchedRing = 4;
 struct SchedRing {
     uint32_t sfull, sempty, tiles;      // shared-memory addresses (this CTA)
@@ -120,7 +121,7 @@ struct SchedRing {
         if (!WARP || lane == 0) mbar_arrive_relaxed_cluster(sempty + slot * 8, lead_rank, (uint32_t)w);
         return w;
     }
-    // leader producer thread: hand item `w` (number `it`) to every consumer of the pair
+    // scheduler thread: hand item `w` (number `it`) to every consumer of the pair
     __device__ __forceinline__ void publish(int it, int w) const {
         const int slot = it & (kSchedRing - 1);
         const uint32_t ph = ((uint32_t)(it - 1) / kSchedRing) & 1u;
