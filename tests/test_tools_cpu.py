@@ -41,3 +41,32 @@ def test_global_plan_with_fewer_items_than_ranks():
     # all padding: nobody encodes anything, the gathered table still has one (zero) row per rank
     p = par.plan_global_batch(np.zeros(8, dtype=np.int64), 4, 1)
     assert p.n_unique == 0 and p.u_max == 1 and p.my_first_slots.size == 0
+
+
+def test_fused_adamw_declares_the_grad_scaler_contract():
+    """torch.amp.GradScaler.step hands itself to optimizers whose step() has a `grad_scaler` parameter and then does NOT
+    run its own pass over the gradients (torch/amp/grad_scaler.py): the signature is the contract"""
+    import inspect
+    from idvs.morec_b200.optim import FusedAdamW
+    params = inspect.signature(FusedAdamW.step).parameters
+    assert "grad_scaler" in params and params["grad_scaler"].default is None
+    assert getattr(FusedAdamW, "_step_supports_amp_scaling", False) is True
+
+
+def test_scoring_arithmetic_follows_the_precision_mode():
+    """Model._ce_inputs: 3xTF32 on fp32 operands in the parity mode, one TF32 pass in tf32, the 16-bit activations as
+    they are in fp16 / bf16 (what autocast does with the logits matmul, model/model.py:49)"""
+    import types
+    import torch
+    from idvs.morec_b200.model import Model
+    a = types.SimpleNamespace(max_seq_len=4, embedding_dim=8, num_attention_heads=2, drop_rate=0.0, transformer_block=1)
+    m = Model(a, 10, False, None, np.ones(11) / 11)
+    P, E = torch.randn(8, 8), torch.randn(10, 8)
+    for mode, dt, x3, out_dt in (("fp32", torch.float32, True, torch.float32), ("tf32", torch.float32, False, torch.float32),
+                                 ("fp16", torch.float16, False, torch.float16), ("bf16", torch.bfloat16, False, torch.bfloat16)):
+        m.compute_dtype = mode
+        meta, p, e = m._ce_inputs(P.to(dt), E.to(dt))
+        assert meta["x3"] is x3 and p.dtype == out_dt and e.dtype == out_dt, mode
+    m.compute_dtype = "fp16"                       # mixed inputs fall back to fp32 operands
+    meta, p, e = m._ce_inputs(P, E.half())
+    assert p.dtype == torch.float32 and e.dtype == torch.float32
